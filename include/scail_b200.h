@@ -1,0 +1,98 @@
+/* scail_b200 — C ABI of the Blackwell-native SCAIL denoising path (libscail_b200.so).
+ *
+ * Boundary contract:
+ *  - every buffer is caller-owned device memory (a PyTorch tensor's data_ptr); the library never
+ *    frees or retains a pointer beyond the call (it caches TMA descriptors keyed on pointer+shape),
+ *  - kernels are enqueued on the caller's stream, no implicit synchronisation,
+ *  - every function returns 0 on success or a negative code; scail_last_error() returns a
+ *    thread-local message.  Nothing here calls exit().
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * The reference (zai-org/SCAIL) has no native code on this path; each entry point names the
+ * PyTorch call sites (reference file:line) whose work it replaces.  The ctypes precedent in the
+ * reference is sat/quantization/kernels.py:70-121 (torch.empty outputs, c_void_p(data_ptr) args,
+ * launch on torch.cuda.current_stream()).
+ */
+#ifndef SCAIL_B200_H
+#define SCAIL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* scail_stream_t; /* cudaStream_t */
+
+const char* scail_last_error(void);
+int scail_version(void);
+/* device properties the host side sizes grids with; returns <0 when no CUDA device is usable */
+int scail_device_sm_count(int device);
+
+/* GEMM epilogues */
+enum {
+    SCAIL_EPI_BIAS = 0,
+    SCAIL_EPI_BIAS_GELU = 1,      /* nn.GELU(approximate="tanh"), dit_video_crossattn_sc_xc.py:1296 */
+    SCAIL_EPI_BIAS_GATE_RES = 2,  /* x + gate * (acc + bias),   dit_video_crossattn_sc_xc.py:1036,1050 */
+    SCAIL_EPI_BIAS_RES = 3,       /* x + (acc + bias),          dit_video_crossattn_sc_xc.py:1042 */
+    SCAIL_EPI_BIAS_SILU = 4,      /* nn.SiLU after linear,      dit_video_crossattn_sc_xc.py:1327-1331 */
+    SCAIL_EPI_BIAS_GELU_ERF = 5   /* nn.GELU() in MLPProj,      dit_video_crossattn_sc_xc.py:38 */
+};
+
+/* C[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W, C bf16 row-major with leading dims lda/ldw/ldc
+ * (elements, multiples of 8).  bias [N] bf16 or NULL; gate [B, gate_stride] bf16 indexed by
+ * row / rows_per_batch; residual [M, ldr] bf16.  c_fp32 != 0 writes float32 C instead.
+ * Replaces ColumnParallelLinear.forward / RowParallelLinear.forward (sat/mpu/layers.py:230-243,
+ * :425-444) and nn.Linear / nn.Conv3d-as-GEMM call sites of the DiT. */
+int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, int epilogue, const void* gate, int64_t gate_stride,
+                    int64_t rows_per_batch, const void* residual, int64_t ldr, int c_fp32, scail_stream_t stream);
+
+/* out = modulate(LayerNorm(x)) per row.  gamma/beta (bf16 [D]) and shift/scale (bf16 [B, mod_stride])
+ * are optional (NULL).  Reads rows [in_row_offset, in_row_offset+rows_out) of each batch of
+ * in_batch_rows rows; writes [B*rows_out, D] densely.  D % 256 == 0, D <= 5120.
+ * Replaces layer.input_layernorm / post_attention_layernorm / post_cross_attention_layernorm /
+ * norm_final + modulate (dit_video_crossattn_sc_xc.py:1031-1032, 1039, 1045-1046, 825, 760-761). */
+int scail_ln_modulate(const void* x, void* out, const void* gamma, const void* beta, const void* shift,
+                      const void* scale, int64_t mod_stride, int64_t B, int64_t rows_out, int64_t in_batch_rows,
+                      int64_t in_row_offset, int64_t D, float eps, scail_stream_t stream);
+
+/* In-place RMSNorm over D columns (fp32 math, affine weight) of 1 or 2 column slabs of a
+ * [rows, ld] bf16 matrix, optionally followed by interleaved-pair RoPE with per-token fp32
+ * tables cos/sin [rows_per_batch, 128].  Replaces RMSNorm.forward (dit_video_crossattn_sc_xc.py:61-68)
+ * on q/k (:1070-1074, :1131-1142) and Rotary3DPositionEmbeddingMixin.attention_fn (:653-757). */
+int scail_rmsnorm_rope(void* buf, int64_t ld, int64_t rows, int64_t rows_per_batch, int64_t D, int nslabs,
+                       int64_t col_offset0, const void* weight0, int64_t col_offset1, const void* weight1,
+                       const float* cos, const float* sin, float eps, scail_stream_t stream);
+
+/* Flash attention, head_dim 128, bf16, non-causal, softmax scale = scale.  Q/K/V are column slabs
+ * (head h at columns [h*128, h*128+128)) of row-major matrices with leading dims ldq/ldk/ldv; batch b
+ * starts at row b*q_batch_rows (Q, out) / b*kv_batch_rows (K, V); q_rows_total / kv_rows_total are the
+ * allocated row counts (TMA bounds).  accumulate != 0 adds into out.
+ * Replaces attention_fn_default -> F.scaled_dot_product_attention (sat/transformer_defaults.py:47-79). */
+int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* out,
+                    int64_t ldo, int64_t B, int64_t H, int64_t q_len, int64_t kv_len, int64_t q_batch_rows,
+                    int64_t kv_batch_rows, int64_t q_rows_total, int64_t kv_rows_total, float scale, int accumulate,
+                    scail_stream_t stream);
+
+/* mod[b, i] = emb[b, i] + param[i]  (shared-AdaLN modulation vectors, dit_video_crossattn_sc_xc.py:1025-1028, 823) */
+int scail_adaln_modulation(const void* emb, const void* param, void* out, int64_t B, int64_t n, scail_stream_t stream);
+int scail_silu(const void* x, void* out, int64_t n, scail_stream_t stream);
+/* timestep_embedding (sgm/modules/diffusionmodules/util.py:207-231): t fp32 [B] -> bf16 [B, dim] (cos||sin) */
+int scail_timestep_embedding(const float* t, void* out, int64_t B, int64_t dim, scail_stream_t stream);
+
+/* Patch gather for ImagePatchEmbeddingMixin (dit_video_crossattn_sc_xc.py:99-130) including the mask
+ * channels appended by DiffusionTransformer.forward (:1468-1503).  x [B,T,16,H,W], ref [Br,1,16,H,W],
+ * pose [Bp,T,16,H/2,W/2] bf16 -> a_main [B,(1+T)*H/2*W/2, 80], a_pose [B, T*H/4*W/4, 80] bf16. */
+int scail_patchify(const void* x, const void* ref, const void* pose, void* a_main, void* a_pose, int64_t B,
+                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, scail_stream_t stream);
+/* unpatchify (dit_video_crossattn_sc_xc.py:764-784): lin [B, T*Hp*Wp, 64] -> out [B, T, 16, 2Hp, 2Wp], bf16 */
+int scail_unpatchify(const void* lin, void* out, int64_t B, int64_t T, int64_t Hp, int64_t Wp, scail_stream_t stream);
+/* x (fp32, n elements) += dsigma * (v_u + scale*(v_c - v_u)), v bf16 [2, n]
+ * (guiders.py:41-45, sampling_utils.py:7-10, sampling.py:960-963) */
+int scail_cfg_euler(float* x, const void* v, int64_t n, float scale, float dsigma, scail_stream_t stream);
+int scail_cast_f32_bf16(const float* x, void* out, int64_t n, scail_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,313 @@
+// C ABI of libscail_b200.so (see include/scail_b200.h).  Host-side launch code: argument checks,
+// TMA descriptor cache, kernel launches on the caller's stream.  No CPU fallback anywhere.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/scail_b200.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SCAIL_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) return fail(-2, "%s: %s", #expr, cudaGetErrorString(_e));   \
+    } while (0)
+
+#define SCAIL_REQUIRE(cond, ...)                   \
+    do {                                           \
+        if (!(cond)) return fail(-1, __VA_ARGS__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows, box_cols;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_rows); mix(k.box_cols);
+        return h;
+    }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols],
+// box_cols * 2 bytes == 128 (SWIZZLE_128B).  Out-of-bounds elements are zero-filled.
+int make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 CUtensorMap* out) {
+    MapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return fail(-1, "TMA operand must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        if (g_maps.size() > 8192) g_maps.clear();
+        g_maps[key] = m;
+    }
+    *out = m;
+    return 0;
+}
+
+int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sm_count;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+    static std::once_flag once;  // one per kernel instantiation
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [&] { err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+    return err == cudaSuccess ? 0 : fail(-2, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(err));
+}
+
+inline int blocks_for(int64_t n, int per) { return static_cast<int>((n + per - 1) / per); }
+
+}  // namespace
+
+extern "C" {
+
+const char* scail_last_error(void) { return g_err; }
+int scail_version(void) { return 100; }
+
+int scail_device_sm_count(int device) {
+    int n = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return fail(-2, "no usable CUDA device: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, int epilogue, const void* gate, int64_t gate_stride,
+                    int64_t rows_per_batch, const void* residual, int64_t ldr, int c_fp32, scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(A && W && C, "gemm: null operand");
+    SCAIL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    SCAIL_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0, "gemm: N, K, lda, ldw must be multiples of 8");
+    SCAIL_REQUIRE(epilogue >= 0 && epilogue <= 5, "gemm: unknown epilogue %d", epilogue);
+    if (epilogue == EPI_BIAS_GATE_RES) SCAIL_REQUIRE(gate && residual && gate_stride % 8 == 0, "gemm: gate/residual required");
+    if (epilogue == EPI_BIAS_RES) SCAIL_REQUIRE(residual, "gemm: residual required");
+    if (residual) SCAIL_REQUIRE(ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
+    CUtensorMap ta, tw;
+    int rc;
+    if ((rc = make_tmap_2d(A, M, K, lda, GEMM_BM, GEMM_BK, &ta))) return rc;
+    if ((rc = make_tmap_2d(W, N, K, ldw, GEMM_BN, GEMM_BK, &tw))) return rc;
+    GemmParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.gate = static_cast<const __nv_bfloat16*>(gate);
+    p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.C = c_fp32 ? nullptr : static_cast<__nv_bfloat16*>(C);
+    p.C32 = c_fp32 ? static_cast<float*>(C) : nullptr;
+    p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
+    p.rows_per_batch = rows_per_batch > 0 ? (int)rows_per_batch : (int)M;
+    p.epilogue = epilogue;
+    p.group_m = 24;
+    if ((rc = set_smem(gemm_bf16_kernel, GEMM_SMEM_BYTES))) return rc;
+    const int num_tiles = blocks_for(M, GEMM_BM) * blocks_for(N, GEMM_BN);
+    const int sms = sm_count();
+    SCAIL_REQUIRE(sms > 0, "gemm: no CUDA device");
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ta, tw, p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_ln_modulate(const void* x, void* out, const void* gamma, const void* beta, const void* shift,
+                      const void* scale, int64_t mod_stride, int64_t B, int64_t rows_out, int64_t in_batch_rows,
+                      int64_t in_row_offset, int64_t D, float eps, scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(x && out, "ln_modulate: null operand");
+    SCAIL_REQUIRE(D % 256 == 0 && D <= ROW_MAXV * 256, "ln_modulate: D=%lld must be a multiple of 256 and <= %d", (long long)D, ROW_MAXV * 256);
+    SCAIL_REQUIRE((gamma == nullptr) == (beta == nullptr) && (shift == nullptr) == (scale == nullptr), "ln_modulate: gamma/beta and shift/scale come in pairs");
+    LnModParams p;
+    p.x = static_cast<const __nv_bfloat16*>(x); p.out = static_cast<__nv_bfloat16*>(out);
+    p.gamma = static_cast<const __nv_bfloat16*>(gamma); p.beta = static_cast<const __nv_bfloat16*>(beta);
+    p.shift = static_cast<const __nv_bfloat16*>(shift); p.scale = static_cast<const __nv_bfloat16*>(scale);
+    p.mod_stride = mod_stride; p.D = (int)D; p.rows_out = (int)rows_out; p.in_batch_rows = (int)in_batch_rows;
+    p.in_row_offset = (int)in_row_offset; p.total_rows = (int)(B * rows_out); p.eps = eps;
+    ln_modulate_kernel<<<blocks_for(p.total_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_rmsnorm_rope(void* buf, int64_t ld, int64_t rows, int64_t rows_per_batch, int64_t D, int nslabs,
+                       int64_t col_offset0, const void* weight0, int64_t col_offset1, const void* weight1,
+                       const float* cos, const float* sin, float eps, scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(buf && weight0 && (nslabs == 1 || (nslabs == 2 && weight1)), "rmsnorm_rope: null operand");
+    SCAIL_REQUIRE(D % 256 == 0 && D <= ROW_MAXV * 256 && ld % 8 == 0 && col_offset0 % 8 == 0 && col_offset1 % 8 == 0, "rmsnorm_rope: bad D/ld/offset");
+    SCAIL_REQUIRE((cos == nullptr) == (sin == nullptr), "rmsnorm_rope: cos/sin come in pairs");
+    RmsRopeParams p;
+    p.buf = static_cast<__nv_bfloat16*>(buf); p.ld = ld;
+    p.col_offset[0] = (int)col_offset0; p.col_offset[1] = (int)col_offset1;
+    p.weight[0] = static_cast<const __nv_bfloat16*>(weight0); p.weight[1] = static_cast<const __nv_bfloat16*>(weight1);
+    p.nslabs = nslabs; p.D = (int)D; p.rows = (int)rows; p.rows_per_batch = (int)rows_per_batch;
+    p.cos = cos; p.sin = sin; p.eps = eps;
+    dim3 grid(blocks_for(rows, 8), nslabs);
+    rmsnorm_rope_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* out,
+                    int64_t ldo, int64_t B, int64_t H, int64_t q_len, int64_t kv_len, int64_t q_batch_rows,
+                    int64_t kv_batch_rows, int64_t q_rows_total, int64_t kv_rows_total, float scale, int accumulate,
+                    scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(Q && K && V && out, "attention: null operand");
+    SCAIL_REQUIRE(B > 0 && H > 0 && q_len > 0 && kv_len > 0, "attention: bad shape");
+    SCAIL_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
+    SCAIL_REQUIRE(q_len <= q_batch_rows && kv_len <= kv_batch_rows && B * q_batch_rows <= q_rows_total + (q_batch_rows - q_len) &&
+                      B * kv_batch_rows <= kv_rows_total + (kv_batch_rows - kv_len),
+                  "attention: row extents inconsistent");
+    CUtensorMap tq, tk, tv;
+    int rc;
+    const uint64_t cols = (uint64_t)H * ATT_D;
+    if ((rc = make_tmap_2d(Q, q_rows_total, cols, ldq, ATT_BQ, 64, &tq))) return rc;
+    if ((rc = make_tmap_2d(K, kv_rows_total, cols, ldk, ATT_BKV, 64, &tk))) return rc;
+    if ((rc = make_tmap_2d(V, kv_rows_total, cols, ldv, ATT_BKV, 64, &tv))) return rc;
+    AttnParams p;
+    p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+    p.q_len = (int)q_len; p.kv_len = (int)kv_len; p.q_batch_rows = (int)q_batch_rows; p.kv_batch_rows = (int)kv_batch_rows;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.accumulate = accumulate;
+    if ((rc = set_smem(attention_fwd_kernel, ATT_SMEM_BYTES))) return rc;
+    dim3 grid(blocks_for(q_len, 2 * ATT_BQ), (unsigned)H, (unsigned)B);
+    attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_adaln_modulation(const void* emb, const void* param, void* out, int64_t B, int64_t n, scail_stream_t stream) {
+    SCAIL_REQUIRE(emb && param && out, "adaln_modulation: null operand");
+    scail::adaln_modulation_kernel<<<blocks_for(B * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(emb), static_cast<const __nv_bfloat16*>(param), static_cast<__nv_bfloat16*>(out), (int)B, (int)n);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_silu(const void* x, void* out, int64_t n, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && out, "silu: null operand");
+    scail::silu_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), (int)n);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_timestep_embedding(const float* t, void* out, int64_t B, int64_t dim, scail_stream_t stream) {
+    SCAIL_REQUIRE(t && out && dim % 2 == 0, "timestep_embedding: bad args");
+    scail::timestep_embedding_kernel<<<blocks_for(B * dim / 2, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        t, static_cast<__nv_bfloat16*>(out), (int)B, (int)dim);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_patchify(const void* x, const void* ref, const void* pose, void* a_main, void* a_pose, int64_t B,
+                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && ref && pose && a_main && a_pose, "patchify: null operand");
+    SCAIL_REQUIRE(H % 4 == 0 && W % 4 == 0 && Br >= 1 && Bp >= 1, "patchify: H, W must be multiples of 4");
+    scail::PatchifyParams p;
+    p.x = static_cast<const __nv_bfloat16*>(x); p.ref = static_cast<const __nv_bfloat16*>(ref);
+    p.pose = static_cast<const __nv_bfloat16*>(pose); p.a_main = static_cast<__nv_bfloat16*>(a_main);
+    p.a_pose = static_cast<__nv_bfloat16*>(a_pose);
+    p.B = (int)B; p.Br = (int)Br; p.Bp = (int)Bp; p.T = (int)T; p.H = (int)H; p.W = (int)W;
+    const int64_t total = B * ((1 + T) * (H / 2) * (W / 2) + T * (H / 4) * (W / 4)) * 20;
+    scail::patchify_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_unpatchify(const void* lin, void* out, int64_t B, int64_t T, int64_t Hp, int64_t Wp, scail_stream_t stream) {
+    SCAIL_REQUIRE(lin && out, "unpatchify: null operand");
+    const int64_t total = B * T * 16 * 4 * Hp * Wp;
+    scail::unpatchify_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(lin), static_cast<__nv_bfloat16*>(out), (int)B, (int)T, (int)Hp, (int)Wp);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_cfg_euler(float* x, const void* v, int64_t n, float scale, float dsigma, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && v, "cfg_euler: null operand");
+    scail::cfg_euler_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<const __nv_bfloat16*>(v), n, scale, dsigma);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_cast_f32_bf16(const float* x, void* out, int64_t n, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && out, "cast: null operand");
+    scail::cast_f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<__nv_bfloat16*>(out), n);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// HBM-bound row / elementwise kernels of the SCAIL DiT step (everything that is not a GEMM or attention).
+// One warp per row, 16-byte vectorised loads, fp32 statistics, bf16 in/out.
+#pragma once
+#include "sm100.cuh"
+
+namespace scail {
+
+constexpr int ROW_MAXV = 20;  // up to 20 uint4 (=160 bf16) per lane -> D <= 5120, D % 256 == 0
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct LnModParams {
+    const __nv_bfloat16* x;      // input rows
+    __nv_bfloat16* out;          // output rows [B*rows_out, D]
+    const __nv_bfloat16* gamma;  // optional affine
+    const __nv_bfloat16* beta;
+    const __nv_bfloat16* shift;  // optional modulation [B, mod_stride]
+    const __nv_bfloat16* scale;
+    int64_t mod_stride;
+    int D;
+    int rows_out;         // rows per batch written
+    int in_batch_rows;    // rows per batch in the input
+    int in_row_offset;    // first input row (within a batch) to read
+    int total_rows;       // B * rows_out
+    float eps;
+};
+
+// LayerNorm (+optional affine) (+optional AdaLN modulate x*(1+scale)+shift).
+// Restates F.layer_norm + modulate (dit_video_crossattn_sc_xc.py:760-761, :1031-1032, :1045-1046, :825).
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= p.total_rows) return;
+    const int b = warp / p.rows_out;
+    const int r = warp - b * p.rows_out;
+    const int64_t in_row = static_cast<int64_t>(b) * p.in_batch_rows + p.in_row_offset + r;
+    const uint4* xin = reinterpret_cast<const uint4*>(p.x + in_row * p.D);
+    const int nvec = p.D >> 8;  // vectors per lane
+    uint4 v[ROW_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < ROW_MAXV; ++j) {
+        if (j < nvec) {
+            v[j] = xin[j * 32 + lane];
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16(w[k]);
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mean = warp_sum(sum) / p.D;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < ROW_MAXV; ++j) {
+        if (j < nvec) {
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16(w[k]);
+                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / p.D + p.eps);
+    uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(warp) * p.D);
+#pragma unroll
+    for (int j = 0; j < ROW_MAXV; ++j) {
+        if (j < nvec) {
+            const int col = (j * 32 + lane) * 8;
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 t = unpack_bf16(w[k]);
+                f[2 * k] = (t.x - mean) * rstd;
+                f[2 * k + 1] = (t.y - mean) * rstd;
+            }
+            if (p.gamma) {
+                uint4 g = *reinterpret_cast<const uint4*>(p.gamma + col);
+                uint4 bb = *reinterpret_cast<const uint4*>(p.beta + col);
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 g2 = unpack_bf16(gw[k]), b2 = unpack_bf16(bw[k]);
+                    f[2 * k] = f[2 * k] * g2.x + b2.x;
+                    f[2 * k + 1] = f[2 * k + 1] * g2.y + b2.y;
+                }
+            }
+            if (p.scale) {
+                uint4 s = *reinterpret_cast<const uint4*>(p.scale + b * p.mod_stride + col);
+                uint4 h = *reinterpret_cast<const uint4*>(p.shift + b * p.mod_stride + col);
+                const uint32_t sw[4] = {s.x, s.y, s.z, s.w}, hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 s2 = unpack_bf16(sw[k]), h2 = unpack_bf16(hw[k]);
+                    f[2 * k] = f[2 * k] * (1.0f + s2.x) + h2.x;
+                    f[2 * k + 1] = f[2 * k + 1] * (1.0f + s2.y) + h2.y;
+                }
+            }
+            uint4 ov;
+            ov.x = pack_bf16(f[0], f[1]);
+            ov.y = pack_bf16(f[2], f[3]);
+            ov.z = pack_bf16(f[4], f[5]);
+            ov.w = pack_bf16(f[6], f[7]);
+            o[j * 32 + lane] = ov;
+        }
+    }
+}
+
+struct RmsRopeParams {
+    __nv_bfloat16* buf;   // [rows, ld] ; normalised in place
+    int64_t ld;
+    int col_offset[2];    // column offset of slab 0 / slab 1 (e.g. q and k inside the fused QKV buffer)
+    const __nv_bfloat16* weight[2];
+    int nslabs;           // 1 or 2
+    int D;                // normalised width (hidden size), D % 256 == 0
+    int rows;             // total rows (B * rows_per_batch)
+    int rows_per_batch;
+    const float* cos;     // optional [rows_per_batch, 128] fp32 tables (token = row % rows_per_batch)
+    const float* sin;
+    float eps;
+};
+
+// RMSNorm over the full hidden width (dit_video_crossattn_sc_xc.py:61-68, F5) fused with the
+// interleaved-pair 3-D RoPE (:336-340, :525-645).  grid.y selects the slab (q / k).
+__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsRopeParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int slab = blockIdx.y;
+    if (warp >= p.rows) return;
+    __nv_bfloat16* base = p.buf + static_cast<int64_t>(warp) * p.ld + p.col_offset[slab];
+    uint4* xin = reinterpret_cast<uint4*>(base);
+    const int nvec = p.D >> 8;
+    uint4 v[ROW_MAXV];
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < ROW_MAXV; ++j) {
+        if (j < nvec) {
+            v[j] = xin[j * 32 + lane];
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf16(w[k]);
+                sq += f.x * f.x + f.y * f.y;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / p.D + p.eps);
+    // head_dim = 128 = 16 vectors: the rope column (col % 128) of lane i is (i % 16) * 8 for every vector j
+    float cs[8], sn[8];
+    const bool rope = p.cos != nullptr;
+    if (rope) {
+        const int tok = warp % p.rows_per_batch;
+        const float4* c4 = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(tok) * 128 + (lane & 15) * 8);
+        const float4* s4 = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(tok) * 128 + (lane & 15) * 8);
+        float4 a = c4[0], bq = c4[1], c = s4[0], d = s4[1];
+        cs[0] = a.x; cs[1] = a.y; cs[2] = a.z; cs[3] = a.w; cs[4] = bq.x; cs[5] = bq.y; cs[6] = bq.z; cs[7] = bq.w;
+        sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w; sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
+    }
+    const __nv_bfloat16* wgt = p.weight[slab];
+#pragma unroll
+    for (int j = 0; j < ROW_MAXV; ++j) {
+        if (j < nvec) {
+            const int col = (j * 32 + lane) * 8;
+            uint4 g = *reinterpret_cast<const uint4*>(wgt + col);
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, gw[4] = {g.x, g.y, g.z, g.w};
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 t = unpack_bf16(w[k]), g2 = unpack_bf16(gw[k]);
+                f[2 * k] = g2.x * (t.x * rstd);
+                f[2 * k + 1] = g2.y * (t.y * rstd);
+            }
+            if (rope) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float x1 = f[2 * k], x2 = f[2 * k + 1];
+                    f[2 * k] = x1 * cs[2 * k] - x2 * sn[2 * k];
+                    f[2 * k + 1] = x2 * cs[2 * k + 1] + x1 * sn[2 * k + 1];
+                }
+            }
+            uint4 ov;
+            ov.x = pack_bf16(f[0], f[1]);
+            ov.y = pack_bf16(f[2], f[3]);
+            ov.z = pack_bf16(f[4], f[5]);
+            ov.w = pack_bf16(f[6], f[7]);
+            xin[j * 32 + lane] = ov;
+        }
+    }
+}
+
+// mod[b, i] = emb[b, i] + param[i]   (dit_video_crossattn_sc_xc.py:1025-1028, :823) fp32 add, one bf16 rounding
+__global__ void adaln_modulation_kernel(const __nv_bfloat16* emb, const __nv_bfloat16* param, __nv_bfloat16* out,
+                                        int B, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * n) return;
+    out[i] = __float2bfloat16(__bfloat162float(emb[i]) + __bfloat162float(param[i % n]));
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = __bfloat162float(x[i]);
+    out[i] = __float2bfloat16(v / (1.0f + expf(-v)));
+}
+
+// sgm/modules/diffusionmodules/util.py:207-231: freqs in fp64, args fp32, cos||sin, cast to bf16
+__global__ void timestep_embedding_kernel(const float* t, __nv_bfloat16* out, int B, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= B * half) return;
+    const int b = i / half, k = i - b * half;
+    const double fr = exp(-log(10000.0) * static_cast<double>(k) / static_cast<double>(half));
+    const float arg = t[b] * static_cast<float>(fr);
+    out[b * dim + k] = __float2bfloat16(cosf(arg));
+    out[b * dim + half + k] = __float2bfloat16(sinf(arg));
+}
+
+struct PatchifyParams {
+    const __nv_bfloat16* x;     // [B, T, 16, H, W]
+    const __nv_bfloat16* ref;   // [Br, 1, 16, H, W]
+    const __nv_bfloat16* pose;  // [Bp, T, 16, H/2, W/2]
+    __nv_bfloat16* a_main;      // [B, (1+T)*H/2*W/2, 80]   rows: ref tokens then noise tokens
+    __nv_bfloat16* a_pose;      // [B, T*H/4*W/4, 80]
+    int B, Br, Bp, T, H, W;
+};
+
+// Patch gather for the two Conv3d(20->d, k=s=(1,2,2)) of ImagePatchEmbeddingMixin
+// (dit_video_crossattn_sc_xc.py:99-130) incl. the mask channels appended in
+// DiffusionTransformer.forward (:1468, :1483-1486, :1496-1503): x gets 4 zero channels,
+// ref and pose get 4 one channels.  A[token, c*4 + p*2 + q] = in[b, t, c, 2y+p, 2x+q].
+__global__ void patchify_kernel(const PatchifyParams p) {
+    const int hp = p.H / 2, wp = p.W / 2, hq = p.H / 4, wq = p.W / 4;
+    const int n_main = (1 + p.T) * hp * wp, n_pose = p.T * hq * wq;
+    const int64_t total = static_cast<int64_t>(p.B) * (n_main + n_pose) * 20;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = i % 20;
+    int64_t tok = i / 20;
+    const int b = tok / (n_main + n_pose);
+    int n = tok - static_cast<int64_t>(b) * (n_main + n_pose);
+    const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.0f);
+    __nv_bfloat16 v[4];
+    __nv_bfloat16* dst;
+    if (n < n_main) {
+        const int t = n / (hp * wp), rem = n - t * hp * wp, y = rem / wp, x = rem - y * wp;
+        dst = p.a_main + (static_cast<int64_t>(b) * n_main + n) * 80 + c * 4;
+        if (c >= 16) {
+            const __nv_bfloat16 m = (t == 0) ? one : zero;
+            v[0] = v[1] = v[2] = v[3] = m;
+        } else {
+            const __nv_bfloat16* src =
+                (t == 0) ? p.ref + ((static_cast<int64_t>(b % p.Br) * 16 + c) * p.H) * p.W
+                         : p.x + (((static_cast<int64_t>(b) * p.T + (t - 1)) * 16 + c) * p.H) * p.W;
+            v[0] = src[(2 * y) * p.W + 2 * x];
+            v[1] = src[(2 * y) * p.W + 2 * x + 1];
+            v[2] = src[(2 * y + 1) * p.W + 2 * x];
+            v[3] = src[(2 * y + 1) * p.W + 2 * x + 1];
+        }
+    } else {
+        n -= n_main;
+        const int t = n / (hq * wq), rem = n - t * hq * wq, y = rem / wq, x = rem - y * wq;
+        dst = p.a_pose + (static_cast<int64_t>(b) * n_pose + n) * 80 + c * 4;
+        if (c >= 16) {
+            v[0] = v[1] = v[2] = v[3] = one;
+        } else {
+            const int H2 = p.H / 2, W2 = p.W / 2;
+            const __nv_bfloat16* src = p.pose + (((static_cast<int64_t>(b % p.Bp) * p.T + t) * 16 + c) * H2) * W2;
+            v[0] = src[(2 * y) * W2 + 2 * x];
+            v[1] = src[(2 * y) * W2 + 2 * x + 1];
+            v[2] = src[(2 * y + 1) * W2 + 2 * x];
+            v[3] = src[(2 * y + 1) * W2 + 2 * x + 1];
+        }
+    }
+    uint2 o;
+    o.x = static_cast<uint32_t>(__bfloat16_as_ushort(v[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(v[1])) << 16);
+    o.y = static_cast<uint32_t>(__bfloat16_as_ushort(v[2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(v[3])) << 16);
+    *reinterpret_cast<uint2*>(dst) = o;
+}
+
+// unpatchify (dit_video_crossattn_sc_xc.py:764-784): lin [B, T*Hp*Wp, 64] with feature order (p q c)
+//   -> out [B, T, 16, 2*Hp, 2*Wp]
+__global__ void unpatchify_kernel(const __nv_bfloat16* lin, __nv_bfloat16* out, int B, int T, int Hp, int Wp) {
+    const int64_t total = static_cast<int64_t>(B) * T * 16 * (2 * Hp) * (2 * Wp);
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int W = 2 * Wp, H = 2 * Hp;
+    const int xx = i % W;
+    const int yy = (i / W) % H;
+    const int c = (i / (static_cast<int64_t>(W) * H)) % 16;
+    const int t = (i / (static_cast<int64_t>(W) * H * 16)) % T;
+    const int b = i / (static_cast<int64_t>(W) * H * 16 * T);
+    const int y = yy >> 1, pp = yy & 1, x = xx >> 1, q = xx & 1;
+    const int64_t tok = (static_cast<int64_t>(b) * T + t) * Hp * Wp + y * Wp + x;
+    out[i] = lin[tok * 64 + (pp * 2 + q) * 16 + c];
+}
+
+// VanillaCFG + Euler update, fp32 (guiders.py:41-45, sampling_utils.py:7-10, sampling.py:960-963):
+// x += dsigma * (u + s*(c-u)), model output v is bf16 [2, n] (uncond, cond)
+__global__ void cfg_euler_kernel(float* x, const __nv_bfloat16* v, int64_t n, float scale, float dsigma) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float u = __bfloat162float(v[i]), c = __bfloat162float(v[n + i]);
+    x[i] = x[i] + dsigma * (u + scale * (c - u));
+}
+
+__global__ void cast_f32_to_bf16_kernel(const float* x, __nv_bfloat16* out, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16(x[i]);
+}
+
+}  // namespace scail

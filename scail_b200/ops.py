@@ -1,0 +1,163 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point).  All tensors must be
+CUDA tensors; there is no CPU path.  Launches go to torch.cuda.current_stream()."""
+import math
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_SILU, EPI_BIAS_GELU_ERF = range(6)
+
+LAUNCHES = 0  # number of library kernels launched through this module (bench.py reports it)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype=torch.bfloat16):
+    if not t.is_cuda:
+        raise RuntimeError("scail_b200 ops need CUDA tensors: there is no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def gemm(a, w, bias=None, out=None, epilogue=EPI_BIAS, gate=None, residual=None, rows_per_batch=0, out_fp32=False):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  a/out may be row-strided 2-D views (stride(1)==1)."""
+    _req(a), _req(w)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    gs = gate.stride(0) if gate is not None else 0
+    _lib.check(_lib.lib().scail_gemm_bf16(
+        _ptr(a), a.stride(0), _ptr(w), w.stride(0), _ptr(bias), _ptr(out), out.stride(0), M, N, K, epilogue,
+        _ptr(gate), gs, rows_per_batch, _ptr(residual), residual.stride(0) if residual is not None else 0,
+        1 if out.dtype == torch.float32 else 0, _stream()), "scail_gemm_bf16")
+    _count()
+    return out
+
+
+def ln_modulate(x, out=None, gamma=None, beta=None, shift=None, scale=None, eps=1e-6, rows_out=None, row_offset=0):
+    """x [B, Nin, D] -> out [B, rows_out, D] = modulate(LN(x[:, row_offset:row_offset+rows_out]))."""
+    _req(x)
+    B, n_in, D = x.shape
+    rows_out = n_in if rows_out is None else rows_out
+    if out is None:
+        out = torch.empty(B, rows_out, D, device=x.device, dtype=torch.bfloat16)
+    assert x.is_contiguous() and out.is_contiguous()
+    ms = shift.stride(0) if shift is not None else 0
+    if shift is not None:
+        assert shift.stride(-1) == 1 and scale.stride(-1) == 1 and scale.stride(0) == ms
+    _lib.check(_lib.lib().scail_ln_modulate(_ptr(x), _ptr(out), _ptr(gamma), _ptr(beta), _ptr(shift), _ptr(scale), ms,
+                                            B, rows_out, n_in, row_offset, D, eps, _stream()), "scail_ln_modulate")
+    _count()
+    return out
+
+
+def rmsnorm_rope(buf, rows_per_batch, D, slabs, cos=None, sin=None, eps=1e-6):
+    """In-place RMSNorm(+RoPE) on column slabs [(col_offset, weight), ...] of the 2-D bf16 matrix buf."""
+    _req(buf)
+    assert buf.dim() == 2 and buf.stride(1) == 1 and 1 <= len(slabs) <= 2
+    (o0, w0) = slabs[0]
+    (o1, w1) = slabs[1] if len(slabs) == 2 else (0, None)
+    _lib.check(_lib.lib().scail_rmsnorm_rope(_ptr(buf), buf.stride(0), buf.shape[0], rows_per_batch, D, len(slabs),
+                                             o0, _ptr(w0), o1, _ptr(w1), _ptr(cos), _ptr(sin), eps, _stream()),
+               "scail_rmsnorm_rope")
+    _count()
+    return buf
+
+
+def attention(q, k, v, out, B, H, q_len, kv_len, q_batch_rows=None, kv_batch_rows=None, scale=None, accumulate=False):
+    """q/k/v/out: 2-D row-strided bf16 views [rows, H*128] (stride(1)==1); head h = columns h*128..h*128+127."""
+    for t in (q, k, v, out):
+        _req(t)
+        assert t.dim() == 2 and t.stride(1) == 1
+    q_batch_rows = q_len if q_batch_rows is None else q_batch_rows
+    kv_batch_rows = kv_len if kv_batch_rows is None else kv_batch_rows
+    scale = 1.0 / math.sqrt(128) if scale is None else scale
+    _lib.check(_lib.lib().scail_attention(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+                                          out.stride(0), B, H, q_len, kv_len, q_batch_rows, kv_batch_rows, q.shape[0],
+                                          k.shape[0], scale, 1 if accumulate else 0, _stream()), "scail_attention")
+    _count()
+    return out
+
+
+def adaln_modulation(emb, param, out=None):
+    _req(emb), _req(param)
+    B, n = emb.shape
+    assert param.numel() == n
+    if out is None:
+        out = torch.empty_like(emb)
+    _lib.check(_lib.lib().scail_adaln_modulation(_ptr(emb), _ptr(param), _ptr(out), B, n, _stream()), "scail_adaln_modulation")
+    _count()
+    return out
+
+
+def silu(x):
+    _req(x)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().scail_silu(_ptr(x), _ptr(out), x.numel(), _stream()), "scail_silu")
+    _count()
+    return out
+
+
+def timestep_embedding(t, dim):
+    _req(t, torch.float32)
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_timestep_embedding(_ptr(t), _ptr(out), t.shape[0], dim, _stream()), "scail_timestep_embedding")
+    _count()
+    return out
+
+
+def patchify(x, ref, pose):
+    """x [B,T,16,H,W], ref [Br,1,16,H,W], pose [Bp,T,16,H/2,W/2] (bf16) -> (a_main [B,n_main,80], a_pose [B,n_pose,80])."""
+    _req(x), _req(ref), _req(pose)
+    B, T, C, H, W = x.shape
+    assert C == 16 and x.is_contiguous() and ref.is_contiguous() and pose.is_contiguous()
+    n_main = (1 + T) * (H // 2) * (W // 2)
+    n_pose = T * (H // 4) * (W // 4)
+    a_main = torch.empty(B, n_main, 80, device=x.device, dtype=torch.bfloat16)
+    a_pose = torch.empty(B, n_pose, 80, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_patchify(_ptr(x), _ptr(ref), _ptr(pose), _ptr(a_main), _ptr(a_pose), B, ref.shape[0],
+                                         pose.shape[0], T, H, W, _stream()), "scail_patchify")
+    _count()
+    return a_main, a_pose
+
+
+def unpatchify(lin, B, T, Hp, Wp):
+    _req(lin)
+    assert lin.is_contiguous() and lin.numel() == B * T * Hp * Wp * 64
+    out = torch.empty(B, T, 16, 2 * Hp, 2 * Wp, device=lin.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_unpatchify(_ptr(lin), _ptr(out), B, T, Hp, Wp, _stream()), "scail_unpatchify")
+    _count()
+    return out
+
+
+def cfg_euler_(x, v, scale, dsigma):
+    """x (fp32, [1,...]) += dsigma * (v[0] + scale * (v[1] - v[0])); v bf16 [2, ...]."""
+    _req(x, torch.float32), _req(v)
+    assert x.is_contiguous() and v.is_contiguous() and v.numel() == 2 * x.numel()
+    _lib.check(_lib.lib().scail_cfg_euler(_ptr(x), _ptr(v), x.numel(), float(scale), float(dsigma), _stream()), "scail_cfg_euler")
+    _count()
+    return x
+
+
+def cast_bf16(x):
+    _req(x, torch.float32)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_cast_f32_bf16(_ptr(x.contiguous()), _ptr(out), x.numel(), _stream()), "scail_cast_f32_bf16")
+    _count()
+    return out
