@@ -81,10 +81,11 @@ int scail_silu(const void* x, void* out, int64_t n, scail_stream_t stream);
 int scail_timestep_embedding(const float* t, void* out, int64_t B, int64_t dim, scail_stream_t stream);
 
 /* Patch gather for ImagePatchEmbeddingMixin (dit_video_crossattn_sc_xc.py:99-130) including the mask
- * channels appended by DiffusionTransformer.forward (:1468-1503).  x [B,T,16,H,W], ref [Br,1,16,H,W],
- * pose [Bp,T,16,H/2,W/2] bf16 -> a_main [B,(1+T)*H/2*W/2, 80], a_pose [B, T*H/4*W/4, 80] bf16. */
+ * channels appended by DiffusionTransformer.forward (:1468-1503) when cin == 16 (x: zeros, ref/pose: ones);
+ * cin == 20 reads them from the inputs.  x [B,T,cin,H,W], ref [Br,1,cin,H,W], pose [Bp,T,cin,H/2,W/2] bf16
+ * -> a_main [B,(1+T)*H/2*W/2, 80], a_pose [B, T*H/4*W/4, 80] bf16 (feature order c*4 + p*2 + q). */
 int scail_patchify(const void* x, const void* ref, const void* pose, void* a_main, void* a_pose, int64_t B,
-                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, scail_stream_t stream);
+                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, int64_t cin, scail_stream_t stream);
 /* unpatchify (dit_video_crossattn_sc_xc.py:764-784): lin [B, T*Hp*Wp, 64] -> out [B, T, 16, 2Hp, 2Wp], bf16 */
 int scail_unpatchify(const void* lin, void* out, int64_t B, int64_t T, int64_t Hp, int64_t Wp, scail_stream_t stream);
 /* x (fp32, n elements) += dsigma * (v_u + scale*(v_c - v_u)), v bf16 [2, n]

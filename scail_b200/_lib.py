@@ -29,7 +29,7 @@ SIGNATURES = {
     "scail_adaln_modulation": [c_p, c_p, c_p, c_i64, c_i64, c_p],
     "scail_silu": [c_p, c_p, c_i64, c_p],
     "scail_timestep_embedding": [c_p, c_p, c_i64, c_i64, c_p],
-    "scail_patchify": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p],
+    "scail_patchify": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p],
     "scail_unpatchify": [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p],
     "scail_cfg_euler": [c_p, c_p, c_i64, c_f, c_f, c_p],
     "scail_cast_f32_bf16": [c_p, c_p, c_i64, c_p],

@@ -271,14 +271,15 @@ int scail_timestep_embedding(const float* t, void* out, int64_t B, int64_t dim, 
 }
 
 int scail_patchify(const void* x, const void* ref, const void* pose, void* a_main, void* a_pose, int64_t B,
-                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, scail_stream_t stream) {
+                   int64_t Br, int64_t Bp, int64_t T, int64_t H, int64_t W, int64_t cin, scail_stream_t stream) {
     SCAIL_REQUIRE(x && ref && pose && a_main && a_pose, "patchify: null operand");
+    SCAIL_REQUIRE(cin == 16 || cin == 20, "patchify: cin must be 16 or 20");
     SCAIL_REQUIRE(H % 4 == 0 && W % 4 == 0 && Br >= 1 && Bp >= 1, "patchify: H, W must be multiples of 4");
     scail::PatchifyParams p;
     p.x = static_cast<const __nv_bfloat16*>(x); p.ref = static_cast<const __nv_bfloat16*>(ref);
     p.pose = static_cast<const __nv_bfloat16*>(pose); p.a_main = static_cast<__nv_bfloat16*>(a_main);
     p.a_pose = static_cast<__nv_bfloat16*>(a_pose);
-    p.B = (int)B; p.Br = (int)Br; p.Bp = (int)Bp; p.T = (int)T; p.H = (int)H; p.W = (int)W;
+    p.B = (int)B; p.Br = (int)Br; p.Bp = (int)Bp; p.T = (int)T; p.H = (int)H; p.W = (int)W; p.cin = (int)cin;
     const int64_t total = B * ((1 + T) * (H / 2) * (W / 2) + T * (H / 4) * (W / 4)) * 20;
     scail::patchify_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     SCAIL_CHECK_CUDA(cudaGetLastError());

@@ -223,12 +223,13 @@ __global__ void timestep_embedding_kernel(const float* t, __nv_bfloat16* out, in
 }
 
 struct PatchifyParams {
-    const __nv_bfloat16* x;     // [B, T, 16, H, W]
-    const __nv_bfloat16* ref;   // [Br, 1, 16, H, W]
-    const __nv_bfloat16* pose;  // [Bp, T, 16, H/2, W/2]
+    const __nv_bfloat16* x;     // [B, T, cin, H, W]
+    const __nv_bfloat16* ref;   // [Br, 1, cin, H, W]
+    const __nv_bfloat16* pose;  // [Bp, T, cin, H/2, W/2]
     __nv_bfloat16* a_main;      // [B, (1+T)*H/2*W/2, 80]   rows: ref tokens then noise tokens
     __nv_bfloat16* a_pose;      // [B, T*H/4*W/4, 80]
     int B, Br, Bp, T, H, W;
+    int cin;  // channels present in the inputs: 16 (mask channels synthesised) or 20 (already appended)
 };
 
 // Patch gather for the two Conv3d(20->d, k=s=(1,2,2)) of ImagePatchEmbeddingMixin
@@ -251,13 +252,13 @@ __global__ void patchify_kernel(const PatchifyParams p) {
     if (n < n_main) {
         const int t = n / (hp * wp), rem = n - t * hp * wp, y = rem / wp, x = rem - y * wp;
         dst = p.a_main + (static_cast<int64_t>(b) * n_main + n) * 80 + c * 4;
-        if (c >= 16) {
+        if (c >= p.cin) {
             const __nv_bfloat16 m = (t == 0) ? one : zero;
             v[0] = v[1] = v[2] = v[3] = m;
         } else {
             const __nv_bfloat16* src =
-                (t == 0) ? p.ref + ((static_cast<int64_t>(b % p.Br) * 16 + c) * p.H) * p.W
-                         : p.x + (((static_cast<int64_t>(b) * p.T + (t - 1)) * 16 + c) * p.H) * p.W;
+                (t == 0) ? p.ref + ((static_cast<int64_t>(b % p.Br) * p.cin + c) * p.H) * p.W
+                         : p.x + (((static_cast<int64_t>(b) * p.T + (t - 1)) * p.cin + c) * p.H) * p.W;
             v[0] = src[(2 * y) * p.W + 2 * x];
             v[1] = src[(2 * y) * p.W + 2 * x + 1];
             v[2] = src[(2 * y + 1) * p.W + 2 * x];
@@ -267,11 +268,11 @@ __global__ void patchify_kernel(const PatchifyParams p) {
         n -= n_main;
         const int t = n / (hq * wq), rem = n - t * hq * wq, y = rem / wq, x = rem - y * wq;
         dst = p.a_pose + (static_cast<int64_t>(b) * n_pose + n) * 80 + c * 4;
-        if (c >= 16) {
+        if (c >= p.cin) {
             v[0] = v[1] = v[2] = v[3] = one;
         } else {
             const int H2 = p.H / 2, W2 = p.W / 2;
-            const __nv_bfloat16* src = p.pose + (((static_cast<int64_t>(b % p.Bp) * p.T + t) * 16 + c) * H2) * W2;
+            const __nv_bfloat16* src = p.pose + (((static_cast<int64_t>(b % p.Bp) * p.T + t) * p.cin + c) * H2) * W2;
             v[0] = src[(2 * y) * W2 + 2 * x];
             v[1] = src[(2 * y) * W2 + 2 * x + 1];
             v[2] = src[(2 * y + 1) * W2 + 2 * x];

@@ -123,16 +123,18 @@ def timestep_embedding(t, dim):
 
 
 def patchify(x, ref, pose):
-    """x [B,T,16,H,W], ref [Br,1,16,H,W], pose [Bp,T,16,H/2,W/2] (bf16) -> (a_main [B,n_main,80], a_pose [B,n_pose,80])."""
+    """x [B,T,C,H,W], ref [Br,1,C,H,W], pose [Bp,T,C,H/2,W/2] (bf16, C = 16 or 20)
+    -> (a_main [B,n_main,80], a_pose [B,n_pose,80]).  C == 16: mask channels are synthesised."""
     _req(x), _req(ref), _req(pose)
     B, T, C, H, W = x.shape
-    assert C == 16 and x.is_contiguous() and ref.is_contiguous() and pose.is_contiguous()
+    assert C in (16, 20) and ref.shape[2] == C and pose.shape[2] == C
+    assert x.is_contiguous() and ref.is_contiguous() and pose.is_contiguous()
     n_main = (1 + T) * (H // 2) * (W // 2)
     n_pose = T * (H // 4) * (W // 4)
     a_main = torch.empty(B, n_main, 80, device=x.device, dtype=torch.bfloat16)
     a_pose = torch.empty(B, n_pose, 80, device=x.device, dtype=torch.bfloat16)
     _lib.check(_lib.lib().scail_patchify(_ptr(x), _ptr(ref), _ptr(pose), _ptr(a_main), _ptr(a_pose), B, ref.shape[0],
-                                         pose.shape[0], T, H, W, _stream()), "scail_patchify")
+                                         pose.shape[0], T, H, W, C, _stream()), "scail_patchify")
     _count()
     return a_main, a_pose
 
