@@ -9,6 +9,7 @@ from . import _lib
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_SILU, EPI_BIAS_GELU_ERF = range(6)
 
 LAUNCHES = 0  # number of library kernels launched through this module (bench.py reports it)
+ATTN_EVENTS = None  # bench.py sets this to a list to collect (start, end) CUDA events of self-attention launches
 
 
 def _ptr(t):
@@ -88,9 +89,16 @@ def attention(q, k, v, out, B, H, q_len, kv_len, q_batch_rows=None, kv_batch_row
     q_batch_rows = q_len if q_batch_rows is None else q_batch_rows
     kv_batch_rows = kv_len if kv_batch_rows is None else kv_batch_rows
     scale = 1.0 / math.sqrt(128) if scale is None else scale
+    ev = None
+    if ATTN_EVENTS is not None and kv_len > 1024:  # self-attention launches only
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _lib.check(_lib.lib().scail_attention(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
                                           out.stride(0), B, H, q_len, kv_len, q_batch_rows, kv_batch_rows, q.shape[0],
                                           k.shape[0], scale, 1 if accumulate else 0, _stream()), "scail_attention")
+    if ev is not None:
+        ev[1].record()
+        ATTN_EVENTS.append(ev)
     _count()
     return out
 
