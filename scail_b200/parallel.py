@@ -1,0 +1,86 @@
+"""Context parallelism for the DiT: tokens of the ref || noise || pose sequence are sharded contiguously over
+the ranks of one process group; every per-token op (LN, GEMMs, RMSNorm/RoPE, cross-attention against the
+replicated text/CLIP keys, MLP) is local, and self-attention needs ONE exchange per block: an NCCL all-gather
+of the post-norm, post-RoPE K and V.  Replaces the reference's Ulysses sequence parallelism
+(sat/mpu/ulysses_attn_layer.py:41-110: 4 all_to_all_single per attention call, 12 per block) — numerically the
+same softmax over the same key set, so parity is checked against the single-GPU path.
+
+The all-gather is issued asynchronously (NCCL stream) right after the K/V projection so that the Q projection
+and its RMSNorm+RoPE overlap the transfer.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class ContextParallel:
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.size = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self._kv = {}
+
+    # ---- token sharding (kernel-free: also exercised on CPU/gloo by tests/test_parallel_cpu.py) ----
+    def local_len(self, n_total):
+        if n_total % self.size:
+            raise ValueError(f"sequence length {n_total} is not divisible by the context-parallel size {self.size}")
+        return n_total // self.size
+
+    def shard_tokens(self, hidden):
+        """[B, N, d] -> this rank's contiguous [B, N/P, d] chunk."""
+        n = self.local_len(hidden.shape[1])
+        return hidden[:, self.rank * n:(self.rank + 1) * n].contiguous()
+
+    def gather_tokens(self, local, n_total):
+        """[B, N/P, d] on every rank -> [B, N, d] on every rank."""
+        B, n, d = local.shape
+        buf = torch.empty(self.size * B, n, d, device=local.device, dtype=local.dtype)  # concatenated along dim 0
+        dist.all_gather_into_tensor(buf, local.contiguous(), group=self.group)
+        return buf.view(self.size, B, n, d).permute(1, 0, 2, 3).reshape(B, n_total, d)
+
+    def rope_slice(self, cos, sin, n_local):
+        s = slice(self.rank * n_local, (self.rank + 1) * n_local)
+        return cos[s], sin[s]
+
+    def kv_buffer(self, B, n_local, d, device, dtype=torch.bfloat16):
+        """[B, P, N/P, 2d]: batch-major so that, after the gather, batch b's keys/values are the contiguous
+        [P*N/P, 2d] matrix the attention kernel addresses with kv_batch_rows = N."""
+        key = (B, n_local, d, str(device), dtype)
+        if key not in self._kv:
+            self._kv = {key: torch.empty(B, self.size, n_local, 2 * d, device=device, dtype=dtype)}
+        return self._kv[key]
+
+    def gather_kv(self, kvbuf, async_op=True):
+        """In-place all-gather per batch element: rank r's slot kvbuf[b, r] is sent, kvbuf[b] receives all."""
+        B, P, n, w = kvbuf.shape
+        works = []
+        for b in range(B):
+            works.append(dist.all_gather_into_tensor(kvbuf[b].view(P * n, w), kvbuf[b, self.rank], group=self.group,
+                                                     async_op=async_op))
+        return works
+
+    # ---- the block's self-attention under CP (kernels) ----
+    def self_attention(self, mixin, attn, h2, B, n_local, d, H, wq, wk, cos, sin, ctx):
+        dev = h2.device
+        P = self.size
+        eps = mixin.layernorm_epsilon
+        cos_l, sin_l = self.rope_slice(cos, sin, n_local)
+        w, bias = attn.query_key_value.weight, attn.query_key_value.bias
+        kvbuf = self.kv_buffer(B, n_local, d, dev)
+        for b in range(B):  # K,V projection straight into this rank's slot of the gather buffer
+            slot = kvbuf[b, self.rank]
+            ops.gemm(h2[b * n_local:(b + 1) * n_local], w[d:], bias[d:], out=slot)
+            ops.rmsnorm_rope(slot, n_local, d, [(0, wk)], cos_l, sin_l, eps=eps)
+        works = self.gather_kv(kvbuf, async_op=True)
+        q = torch.empty(B * n_local, d, device=dev, dtype=torch.bfloat16) if not hasattr(self, "_q") or \
+            self._q.shape != (B * n_local, d) or self._q.device != dev else self._q
+        self._q = q
+        ops.gemm(h2, w[:d], bias[:d], out=q)  # overlaps the all-gather
+        ops.rmsnorm_rope(q, n_local, d, [(0, wq)], cos_l, sin_l, eps=eps)
+        for wk_ in works:
+            wk_.wait()
+        kv2 = kvbuf.view(B * P * n_local, 2 * d)
+        ops.attention(q, kv2[:, :d], kv2[:, d:], ctx, B, H, n_local, P * n_local, q_batch_rows=n_local,
+                      kv_batch_rows=P * n_local)
+        return ctx
