@@ -93,6 +93,29 @@ int scail_unpatchify(const void* lin, void* out, int64_t B, int64_t T, int64_t H
 int scail_cfg_euler(float* x, const void* v, int64_t n, float scale, float dsigma, scail_stream_t stream);
 int scail_cast_f32_bf16(const float* x, void* out, int64_t n, scail_stream_t stream);
 
+/* ---- Wan2.1 VAE decode (sgm/models/wan_vae.py); activations channels-last bf16 [T, H, W, C] ---- */
+enum { SCAIL_CONV_EPI_BIAS = 0, SCAIL_CONV_EPI_BIAS_RES = 1, SCAIL_CONV_EPI_HEAD_CLAMP = 2 };
+
+/* Causal 3-D convolution as an implicit GEMM on tcgen05 (CausalConv3d.forward, wan_vae.py:17-36; also the
+ * per-frame Conv2d 3x3 of Resample with KT = 1, :77-83).  x [T,H,W,Cin]; w2 = weight repacked to
+ * [Cout, KT*KH*KW*Cin] (tap-major, channel-minor); stride 1, "same" spatial zero padding, causal temporal
+ * padding (KT-1 zero frames on the left).  Output column c is written to frame t*fmul + c/ocols, channel
+ * c%ocols of out [*, H, W, ldo] (fmul=2, ocols=Cout/2 interleaves time_conv's channel halves as frames,
+ * wan_vae.py:134-137).  epilogue: +bias | +bias+residual [T,H,W,ldr] (ResidualBlock, :220) |
+ * head: +bias, clamp(-1,1), fp32 planes [Cout, T, H, W] (:421, :662-664). */
+int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin, const void* w2, int64_t Cout, int KT,
+                    int KH, int KW, const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                    int64_t ocols, int fmul, int epilogue, scail_stream_t stream);
+/* RMS_norm over channels (F.normalize * sqrt(C) * gamma, wan_vae.py:39-54), optional SiLU; [npix, C] bf16 */
+int scail_rmsnorm_cl(const void* x, const void* gamma, void* out, int64_t npix, int64_t C, int silu, scail_stream_t stream);
+/* nearest-exact 2x spatial upsample (wan_vae.py:57-63): [frames,H,W,C] -> [frames,2H,2W,C] */
+int scail_upsample2x_cl(const void* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, scail_stream_t stream);
+/* z [16,T,h,w] bf16 -> z / inv_std + mean, channels-last [T,h,w,16] (WanVAE_.decode, wan_vae.py:547-551) */
+int scail_vae_latent_to_cl(const void* z, const float* mean, const float* inv_std, void* out, int64_t T, int64_t h,
+                           int64_t w, scail_stream_t stream);
+/* p = softmax(s * scale) per row; s fp32 [rows, cols] -> p bf16 (mid-block attention, wan_vae.py:252-256) */
+int scail_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, float scale, scail_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

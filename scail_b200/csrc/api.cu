@@ -12,6 +12,7 @@
 
 #include "../../include/scail_b200.h"
 #include "attention.cuh"
+#include "conv.cuh"
 #include "gemm.cuh"
 #include "rowops.cuh"
 
@@ -110,6 +111,51 @@ int make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uin
     return 0;
 }
 
+// 4-D bf16 channels-last activation [T, H, W, C]: dims (C, W, H, T), box (64, 16, 8, 1), SWIZZLE_128B.
+// Out-of-bounds box elements (channel tail, spatial halo, t < 0) are zero-filled.
+struct Map4Key {
+    const void* ptr; uint64_t T, H, W, C;
+    bool operator==(const Map4Key& o) const { return ptr == o.ptr && T == o.T && H == o.H && W == o.W && C == o.C; }
+};
+struct Map4KeyHash {
+    size_t operator()(const Map4Key& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.T); mix(k.H); mix(k.W); mix(k.C);
+        return h;
+    }
+};
+std::unordered_map<Map4Key, CUtensorMap, Map4KeyHash> g_maps4;
+
+int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t C, CUtensorMap* out) {
+    Map4Key key{ptr, T, H, W, C};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        auto it = g_maps4.find(key);
+        if (it != g_maps4.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C % 8)) return fail(-1, "conv input must be 16-byte aligned with C %% 8 == 0");
+    cuuint64_t gdim[4] = {C, W, H, T};
+    cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled(4d) failed (%d) T=%llu H=%llu W=%llu C=%llu", (int)r,
+                                        (unsigned long long)T, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        if (g_maps4.size() > 4096) g_maps4.clear();
+        g_maps4[key] = m;
+    }
+    *out = m;
+    return 0;
+}
+
 int g_sm_count = 0;
 int sm_count() {
     if (g_sm_count == 0) {
@@ -120,15 +166,39 @@ int sm_count() {
     return g_sm_count;
 }
 
+std::unordered_map<const void*, cudaError_t> g_smem_done;  // keyed by kernel address (instantiations share a type)
 template <typename K>
 int set_smem(K kernel, int bytes) {
-    static std::once_flag once;  // one per kernel instantiation
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [&] { err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+    const void* key = reinterpret_cast<const void*>(kernel);
+    cudaError_t err;
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        auto it = g_smem_done.find(key);
+        if (it == g_smem_done.end()) {
+            err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            g_smem_done[key] = err;
+        } else {
+            err = it->second;
+        }
+    }
     return err == cudaSuccess ? 0 : fail(-2, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(err));
 }
 
 inline int blocks_for(int64_t n, int per) { return static_cast<int>((n + per - 1) / per); }
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const scail::ConvParams& p, cudaStream_t st) {
+    using namespace scail;
+    int rc;
+    if ((rc = set_smem(conv3d_kernel<BN>, ConvCfg<BN>::SMEM_BYTES))) return rc;
+    const int tiles = p.T * blocks_for(p.H, CONV_PH) * blocks_for(p.W, CONV_PW) * blocks_for(p.Cout, BN);
+    const int sms = sm_count();
+    if (sms <= 0) return fail(-2, "conv3d: no CUDA device");
+    conv3d_kernel<BN><<<tiles < sms ? tiles : sms, CONV_THREADS, ConvCfg<BN>::SMEM_BYTES, st>>>(tx, tw, p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 
 }  // namespace
 
@@ -307,6 +377,73 @@ int scail_cast_f32_bf16(const float* x, void* out, int64_t n, scail_stream_t str
     SCAIL_REQUIRE(x && out, "cast: null operand");
     scail::cast_f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, static_cast<__nv_bfloat16*>(out), n);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin, const void* w2, int64_t Cout, int KT,
+                    int KH, int KW, const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                    int64_t ocols, int fmul, int epilogue, scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(x && w2 && out, "conv3d: null operand");
+    SCAIL_REQUIRE(T > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout > 0, "conv3d: bad shape");
+    SCAIL_REQUIRE(KT >= 1 && KT <= 3 && KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3 && (KH & 1) && (KW & 1), "conv3d: taps must be 1 or 3");
+    SCAIL_REQUIRE(epilogue >= 0 && epilogue <= 2, "conv3d: unknown epilogue");
+    if (epilogue == CONV_EPI_BIAS_RES) SCAIL_REQUIRE(residual && ldr % 8 == 0, "conv3d: residual required");
+    if (epilogue == CONV_EPI_HEAD_CLAMP) SCAIL_REQUIRE(bias && Cout <= 16, "conv3d: head epilogue needs bias and Cout <= 16");
+    else SCAIL_REQUIRE(Cout % 8 == 0 && ldo % 8 == 0 && ocols > 0 && ocols % 8 == 0, "conv3d: Cout, ldo, ocols must be multiples of 8");
+    const int taps = KT * KH * KW;
+    CUtensorMap tx, tw;
+    int rc;
+    if ((rc = make_tmap_cl4d(x, T, H, W, Cin, &tx))) return rc;
+    const int BN = Cout <= 16 ? 16 : (Cout <= 96 ? 96 : 192);
+    if ((rc = make_tmap_2d(w2, Cout, (uint64_t)taps * Cin, (uint64_t)taps * Cin, BN, 64, &tw))) return rc;
+    ConvParams p;
+    p.T = (int)T; p.H = (int)H; p.W = (int)W; p.Cin = (int)Cin; p.Cout = (int)Cout; p.KT = KT; p.KH = KH; p.KW = KW;
+    p.bias = static_cast<const __nv_bfloat16*>(bias); p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.out = out; p.ldo = ldo; p.ldr = ldr; p.ocols = (int)(ocols > 0 ? ocols : Cout); p.fmul = fmul > 0 ? fmul : 1;
+    p.epilogue = epilogue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (BN == 16) return launch_conv<16>(tx, tw, p, st);
+    if (BN == 96) return launch_conv<96>(tx, tw, p, st);
+    return launch_conv<192>(tx, tw, p, st);
+}
+
+int scail_rmsnorm_cl(const void* x, const void* gamma, void* out, int64_t npix, int64_t C, int silu, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && gamma && out, "rmsnorm_cl: null operand");
+    SCAIL_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8192, "rmsnorm_cl: C must be a multiple of 8");
+    const int G = (int)C / 8, ppb = 1024 / G;
+    SCAIL_REQUIRE(ppb >= 1, "rmsnorm_cl: C too large");
+    const int grid = blocks_for(npix, ppb);
+    auto st = static_cast<cudaStream_t>(stream);
+    if (silu) scail::rmsnorm_cl_kernel<true><<<grid, 256, ppb * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(out), npix, (int)C);
+    else scail::rmsnorm_cl_kernel<false><<<grid, 256, ppb * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(out), npix, (int)C);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_upsample2x_cl(const void* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, scail_stream_t stream) {
+    SCAIL_REQUIRE(x && out && C % 8 == 0, "upsample2x_cl: bad args");
+    const int64_t total = frames * 4 * H * W * (C / 8);
+    scail::upsample2x_cl_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), frames, (int)H, (int)W, (int)(C / 8));
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_vae_latent_to_cl(const void* z, const float* mean, const float* inv_std, void* out, int64_t T, int64_t h,
+                           int64_t w, scail_stream_t stream) {
+    SCAIL_REQUIRE(z && mean && inv_std && out, "vae_latent_to_cl: null operand");
+    scail::vae_latent_to_cl_kernel<<<blocks_for(T * h * w * 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), mean, inv_std, static_cast<__nv_bfloat16*>(out), (int)T, (int)h, (int)w);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, float scale, scail_stream_t stream) {
+    SCAIL_REQUIRE(s && p && rows > 0 && cols > 0, "softmax_rows: bad args");
+    scail::softmax_rows_kernel<<<blocks_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        s, static_cast<__nv_bfloat16*>(p), (int)rows, (int)cols, scale);
     SCAIL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

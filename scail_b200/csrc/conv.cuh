@@ -187,15 +187,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                     }
                     continue;
                 }
-                const int fr = t * p.fmul + col0 / p.ocols;
-                const int ch0 = col0 % p.ocols;
-                const int64_t pix = (static_cast<int64_t>(fr) * p.H + h) * p.W + w;
-                __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + ch0;
-                const __nv_bfloat16* rrow = p.residual ? p.residual + pix * p.ldr + ch0 : nullptr;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const int col = col0 + g * 8;
                     if (col < p.Cout) {
+                        const int fr = t * p.fmul + col / p.ocols;
+                        const int64_t pix = (static_cast<int64_t>(fr) * p.H + h) * p.W + w;
+                        __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col % p.ocols;
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
@@ -210,7 +208,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                             }
                         }
                         if (p.epilogue == CONV_EPI_BIAS_RES) {
-                            uint4 rv = *reinterpret_cast<const uint4*>(rrow + g * 8);
+                            uint4 rv = *reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + col % p.ocols);
                             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -224,7 +222,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                         ov.y = pack_bf16(f[2], f[3]);
                         ov.z = pack_bf16(f[4], f[5]);
                         ov.w = pack_bf16(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(orow + g * 8) = ov;
+                        *reinterpret_cast<uint4*>(orow) = ov;
                     }
                 }
             }
@@ -254,7 +252,8 @@ __global__ void __launch_bounds__(256) rmsnorm_cl_kernel(const __nv_bfloat16* x,
     const int G = C >> 3;                 // uint4 vectors per pixel
     const int pix_per_block = 1024 / G;   // <= 1024 vectors per block iteration (4 per thread)
     const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
-    const int nvec = static_cast<int>(min<int64_t>(pix_per_block, npix - pix0)) * G;
+    const int64_t rem = npix - pix0;
+    const int nvec = static_cast<int>(rem < pix_per_block ? rem : pix_per_block) * G;
     for (int i = threadIdx.x; i < pix_per_block; i += blockDim.x) ssq[i] = 0.f;
     __syncthreads();
     const uint4* xin = reinterpret_cast<const uint4*>(x + pix0 * C);

@@ -171,3 +171,75 @@ def cast_bf16(x):
     _lib.check(_lib.lib().scail_cast_f32_bf16(_ptr(x.contiguous()), _ptr(out), x.numel(), _stream()), "scail_cast_f32_bf16")
     _count()
     return out
+
+
+# ---------------------------------------------------------------- Wan2.1 VAE decode ops (channels-last)
+CONV_EPI_BIAS, CONV_EPI_BIAS_RES, CONV_EPI_HEAD_CLAMP = range(3)
+
+
+def conv3d_cl(x, w2, bias, kt, kh, kw, cout, out=None, residual=None, fmul=1, ocols=None, head=False):
+    """x [T,H,W,Cin] bf16 channels-last; w2 [cout, kt*kh*kw*Cin] bf16.  Returns out [T*fmul,H,W,ocols] bf16
+    (or fp32 planes [cout,T,H,W] when head=True)."""
+    _req(x), _req(w2)
+    T, H, W, Cin = x.shape
+    assert x.is_contiguous() and w2.is_contiguous() and w2.shape == (cout, kt * kh * kw * Cin)
+    ocols = cout if ocols is None else ocols
+    if head:
+        if out is None:
+            out = torch.empty(cout, T, H, W, device=x.device, dtype=torch.float32)
+        epi, ldo = CONV_EPI_HEAD_CLAMP, 0
+    else:
+        if out is None:
+            out = torch.empty(T * fmul, H, W, ocols, device=x.device, dtype=torch.bfloat16)
+        epi, ldo = (CONV_EPI_BIAS_RES if residual is not None else CONV_EPI_BIAS), out.shape[-1]
+        assert out.is_contiguous()
+    _lib.check(_lib.lib().scail_conv3d_cl(_ptr(x), T, H, W, Cin, _ptr(w2), cout, kt, kh, kw, _ptr(bias), _ptr(residual),
+                                          residual.shape[-1] if residual is not None else 0, _ptr(out), ldo, ocols, fmul,
+                                          epi, _stream()), "scail_conv3d_cl")
+    _count()
+    return out
+
+
+def rmsnorm_cl(x, gamma, silu=True, out=None):
+    _req(x), _req(gamma)
+    C = x.shape[-1]
+    assert x.is_contiguous() and gamma.numel() == C
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().scail_rmsnorm_cl(_ptr(x), _ptr(gamma), _ptr(out), x.numel() // C, C, 1 if silu else 0, _stream()),
+               "scail_rmsnorm_cl")
+    _count()
+    return out
+
+
+def upsample2x_cl(x):
+    _req(x)
+    Fr, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty(Fr, 2 * H, 2 * W, C, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_upsample2x_cl(_ptr(x), _ptr(out), Fr, H, W, C, _stream()), "scail_upsample2x_cl")
+    _count()
+    return out
+
+
+def vae_latent_to_cl(z, mean, inv_std):
+    """z [16,T,h,w] bf16 -> [T,h,w,16] bf16 = z / inv_std + mean."""
+    _req(z), _req(mean, torch.float32), _req(inv_std, torch.float32)
+    C, T, h, w = z.shape
+    assert C == 16 and z.is_contiguous()
+    out = torch.empty(T, h, w, 16, device=z.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_vae_latent_to_cl(_ptr(z), _ptr(mean), _ptr(inv_std), _ptr(out), T, h, w, _stream()),
+               "scail_vae_latent_to_cl")
+    _count()
+    return out
+
+
+def softmax_rows(s, scale, out=None):
+    _req(s, torch.float32)
+    rows, cols = s.shape
+    assert s.is_contiguous()
+    if out is None:
+        out = torch.empty(rows, cols, device=s.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().scail_softmax_rows(_ptr(s), _ptr(out), rows, cols, float(scale), _stream()), "scail_softmax_rows")
+    _count()
+    return out

@@ -12,8 +12,8 @@ Outputs (committed, small):
   tests/golden/dit_index.pt    — integer-coded index maps: patchify order, unpatchify scatter,
                                  the three RoPE tables (incl. the pooled, W-shifted pose table).
   tests/golden/sampler.pt      — sigma schedule make_flow_timesteps(0,50,shift 5), CFG+Euler step.
-  tests/golden/vae_small.pt    — WanVAE_ decode of a [1,16,3,8,8] latent (dim=32 narrow variant
-                                 + dim=96 full-width), state_dict + output.
+  tests/golden/vae_small.pt    — WanVAE_ decode of a [1,16,3,8,8] latent (dim=16 narrow variant
+                                 of the same architecture), state_dict + output.
 The GPU box never runs this (no /root/reference there); tests read the .pt files.
 """
 import os
@@ -131,7 +131,7 @@ def gen_dit():
 @torch.no_grad()
 def gen_vae():
     res = {}
-    for tag, dim, shape in (("narrow", 32, (1, 16, 3, 8, 8)), ("full", 96, (1, 16, 2, 4, 4))):
+    for tag, dim, shape in (("narrow", 16, (1, 16, 3, 8, 8)),):
         vae = H.build_reference_vae(seed=7, dim=dim)
         g = torch.Generator().manual_seed(11)
         z = torch.randn(*shape, generator=g).to(torch.bfloat16).float()
@@ -139,7 +139,7 @@ def gen_vae():
         out = vae.decode(z, scale).float().clamp_(-1, 1)
         sd = {k: v.to(torch.bfloat16) for k, v in vae.state_dict().items()
               if k.startswith("decoder.") or k.startswith("conv2.")}
-        res[tag] = {"dim": dim, "z": z, "out": out.to(torch.float16) if tag == "full" else out, "state_dict": sd}
+        res[tag] = {"dim": dim, "z": z, "out": out, "state_dict": sd}
         print("vae", tag, tuple(out.shape), float(out.abs().mean()))
     torch.save(res["narrow"], os.path.join(OUT, "vae_small.pt"))
     return res
