@@ -205,6 +205,13 @@ class ImagePatchEmbeddingMixin(BaseMixin):
         self.proj = nn.Conv3d(in_channels, hidden_size, kernel_size=tuple(patch_size), stride=tuple(patch_size), bias=bias)
         self.proj_pose = nn.Conv3d(in_channels, hidden_size, kernel_size=tuple(patch_size), stride=tuple(patch_size), bias=bias)
 
+    def reinit(self, parent_model=None):  # dit_video_crossattn_sc_xc.py:132-136
+        w = self.proj.weight.data
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        nn.init.constant_(self.proj.bias, 0)
+        if hasattr(self.transformer, "word_embeddings"):
+            del self.transformer.word_embeddings
+
     def word_embedding_forward(self, input_ids, **kwargs):
         images, ref, pose = kwargs["images"], kwargs["ref_concat"], kwargs["concat_smpl_render"]
         _need_cuda(images)

@@ -1,0 +1,119 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the product path
+refuses to run without CUDA (no CPU fallback), RoPE tables are bit-identical to the oracle, parameter names match
+the reference's, and — where /root/reference is present — the mixins are accepted by the reference's own
+DiffusionTransformer through the YAML `target:` plug-in mechanism."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_cabi_exports_every_declared_symbol():
+    from scail_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "scail_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(scail_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 18
+    h = _lib.lib()
+    for name in declared:
+        assert hasattr(h, name), name
+    assert declared - {"scail_last_error"} == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert h.scail_version() == 100
+
+
+def test_no_cpu_fallback():
+    from scail_b200 import ops
+    from scail_b200.dit import DiffusionTransformer
+    from scail_b200.wan_vae import WanVAE
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    m = DiffusionTransformer(hidden_size=256, num_attention_heads=2, inner_hidden_size=512, num_layers=1, text_dim=64,
+                             time_embed_dim=256)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 16, 8, 8), timesteps=torch.zeros(1), context=torch.zeros(1, 4, 64),
+          ref_concat=torch.zeros(1, 1, 16, 8, 8), concat_smpl_render=torch.zeros(1, 2, 16, 4, 4),
+          image_clip_features=torch.zeros(1, 257, 1280))
+    v = WanVAE(dim=16, device="cpu")
+    with pytest.raises(RuntimeError):
+        v.decode([torch.zeros(16, 1, 4, 4)])
+    if not torch.cuda.is_available():  # without a device the library itself reports the failure
+        from scail_b200 import _lib
+        assert _lib.lib().scail_device_sm_count(0) < 0
+        assert b"CUDA" in _lib.lib().scail_last_error()
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scail_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_rope_tables_bit_identical_to_oracle():
+    from oracle import dit_oracle as O
+    from scail_b200 import rope
+    for (T, H, W) in [(3, 4, 6), (4, 8, 8), (21, 32, 32)]:
+        c, s = rope.build_tables_cpu(128, T, H, W)
+        c2, s2 = O.rope_tables(128, T, H, W, 21, 150, 150)
+        assert torch.equal(c, c2) and torch.equal(s, s2)
+    c, s = rope.build_tables_cpu(128, 2, 4, 4, 2, 4)  # SP-style shifts (dit_video_crossattn_sc_xc.py:1578-1585)
+    c2, s2 = O.rope_tables(128, 2, 4, 4, 21, 150, 150, h_shift=2, w_shift=4)
+    assert torch.equal(c, c2) and torch.equal(s, s2)
+
+
+def test_state_dict_names_match_reference_golden():
+    from scail_b200.dit import DiffusionTransformer
+    from scail_b200.wan_vae import WanVAE
+    g = torch.load(os.path.join(GOLD, "dit_c1.pt"))
+    cfg = g["cfg"]
+    m = DiffusionTransformer(hidden_size=cfg["hidden"], num_attention_heads=cfg["heads"], inner_hidden_size=cfg["inner"],
+                             num_layers=cfg["layers"], text_dim=cfg["text_dim"], time_embed_dim=cfg["hidden"])
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in g["state_dict"].items()}
+    assert ours == ref
+    gv = torch.load(os.path.join(GOLD, "vae_small.pt"))
+    v = WanVAE(dim=gv["dim"], device="cpu")
+    ours = {k: tuple(t.shape) for k, t in v.model.state_dict().items()}
+    assert ours == {k: tuple(t.shape) for k, t in gv["state_dict"].items()}
+
+
+def test_sampler_schedule_matches_golden():
+    from scail_b200 import sampler
+    s = torch.load(os.path.join(GOLD, "sampler.pt"))
+    assert torch.equal(sampler.make_flow_timesteps(50, 5.0), s["sigmas"])
+
+
+def test_bench_flop_model():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.seq_len() == 27904
+    assert abs(bench.block_flops(27904) / 1e12 - 33.144) < 0.01
+    assert abs(bench.forward_flops(27904) / 1e12 - 1325.8) < 0.1
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/dit_video_crossattn_sc_xc.py"), reason="reference not mounted")
+def test_mixins_plug_into_reference_model():
+    """instantiate_from_config resolves the YAML target strings to scail_b200.dit.*; the reference's
+    DiffusionTransformer._build_modules / BaseModel.collect_hooks_ accept them and the resulting model has
+    exactly the reference's parameter names and shapes."""
+    from oracle import ref_harness as H
+    H.setup()
+    import dit_video_crossattn_sc_xc as ref
+    import importlib
+    import scail_b200.dit as ours
+    importlib.reload(ours)  # pick up sat's BaseMixin now that SAT is importable
+    stock = ref.DiffusionTransformer(**H.dit_config())
+    mine = ref.DiffusionTransformer(**H.dit_config(mixin_module="scail_b200.dit"))
+    assert isinstance(mine.mixins["adaln_layer"], ours.AdaLNMixin)
+    a = {k: tuple(v.shape) for k, v in stock.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    assert a == b
+    for hook in ("word_embedding_forward", "layer_forward", "final_forward", "position_embedding_forward",
+                 "attention_forward", "cross_attention_forward"):
+        assert hook in mine.hooks, hook
+    importlib.reload(ours)
