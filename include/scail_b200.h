@@ -27,6 +27,8 @@ const char* scail_last_error(void);
 int scail_version(void);
 /* device properties the host side sizes grids with; returns <0 when no CUDA device is usable */
 int scail_device_sm_count(int device);
+/* perf experiments only: int64[64*8] device buffer receiving clock64 stamps of attention CTA (0,0,0); NULL disables */
+int scail_debug_set_attention_trace(void* buf);
 
 /* GEMM epilogues */
 enum {

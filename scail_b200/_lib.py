@@ -20,6 +20,7 @@ c_p, c_i64, c_int, c_f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c
 SIGNATURES = {
     "scail_version": [],
     "scail_device_sm_count": [c_int],
+    "scail_debug_set_attention_trace": [c_p],
     "scail_gemm_bf16": [c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p, c_i64, c_i64, c_p,
                         c_i64, c_int, c_p],
     "scail_ln_modulate": [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f, c_p],

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -156,6 +157,7 @@ int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t
     return 0;
 }
 
+long long* g_attn_trace = nullptr;  // perf experiments only
 int g_sm_count = 0;
 int sm_count() {
     if (g_sm_count == 0) {
@@ -206,6 +208,11 @@ extern "C" {
 
 const char* scail_last_error(void) { return g_err; }
 int scail_version(void) { return 100; }
+
+int scail_debug_set_attention_trace(void* buf) {
+    g_attn_trace = static_cast<long long*>(buf);
+    return 0;
+}
 
 int scail_device_sm_count(int device) {
     int n = 0;
@@ -309,6 +316,9 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
     p.q_len = (int)q_len; p.kv_len = (int)kv_len; p.q_batch_rows = (int)q_batch_rows; p.kv_batch_rows = (int)kv_batch_rows;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.accumulate = accumulate;
+    p.trace = g_attn_trace;
+    static const int dbg = getenv("SCAIL_ATTN_DEBUG") ? atoi(getenv("SCAIL_ATTN_DEBUG")) : 0;
+    p.debug = dbg;
     if ((rc = set_smem(attention_fwd_kernel, ATT_SMEM_BYTES))) return rc;
     dim3 grid(blocks_for(q_len, 2 * ATT_BQ), (unsigned)H, (unsigned)B);
     attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);

@@ -23,7 +23,8 @@ constexpr int ATT_BKV = 128;
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: one 128x128 bf16 tile (two 64-column halves)
 constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle warps}
+constexpr int ATT_POLY_EVERY = 4;  // every 4th column pair takes the FMA-pipe exp2 (0 = never)
 constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 
 struct AttnParams {
@@ -35,7 +36,92 @@ struct AttnParams {
     int kv_batch_rows;   // row stride between batches in the K/V matrices
     float scale_log2;    // softmax scale * log2(e)
     int accumulate;      // out += result (second cross-attention pass, dit_video_crossattn_sc_xc.py:1197)
+    long long* trace;    // perf experiments only: per-iteration clock64 stamps of CTA (0,0,0), or null
+    int debug;           // perf experiments only (SCAIL_ATTN_DEBUG): 1 = softmax skips its math, 2 = MMA ignores P barriers
 };
+
+// One 128x128 score tile of one softmax warp (thread = row): TMEM S -> running max (lazy O rescale) -> exp2 ->
+// bf16 P back into TMEM.  MASK = this is the partial last KV tile.
+template <bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t s_tmem, uint32_t o_tmem, float scale_log2, int valid, int j,
+                                             float& m_run, float& l_run, uint32_t bar_pfull) {
+    uint32_t s0[32], s1[32], s2[32], s3[32];
+    tmem_ld_32x32(s_tmem + 0, s0);
+    tmem_ld_32x32(s_tmem + 32, s1);
+    tmem_ld_32x32(s_tmem + 64, s2);
+    tmem_ld_32x32(s_tmem + 96, s3);
+    tmem_ld_wait();
+    if constexpr (MASK) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (c >= valid) s0[c] = 0xff800000u;
+            if (c + 32 >= valid) s1[c] = 0xff800000u;
+            if (c + 64 >= valid) s2[c] = 0xff800000u;
+            if (c + 96 >= valid) s3[c] = 0xff800000u;
+        }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])),
+                             fmaxf(__uint_as_float(s2[c]), __uint_as_float(s3[c]))));
+    }
+    const float m_new = fmaxf(m_run, mx * scale_log2);
+    const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
+    if (__any_sync(0xffffffffu, need)) {
+        const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32(o_tmem + c * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                tmem_st_32x32(o_tmem + c * 32, o);
+            }
+        }
+    }
+    const float neg_m = -m_run;
+    const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+    uint64_t sum_a = 0ull, sum_b = 0ull;  // packed (0.f, 0.f)
+#define SCAIL_ATT_P_CHUNK(SRC, CH)                                                                          \
+    {                                                                                               \
+        uint32_t pk[16];                                                                            \
+        _Pragma("unroll") for (int c = 0; c < 16; ++c) {                                            \
+            const uint64_t y2 = fma_f32x2(pack_f32x2(__uint_as_float(SRC[2 * c]), __uint_as_float(SRC[2 * c + 1])), sc2, nm2); \
+            float e0, e1;                                                                           \
+            if (ATT_POLY_EVERY > 0 && (c % (ATT_POLY_EVERY > 0 ? ATT_POLY_EVERY : 1)) == ATT_POLY_EVERY - 1) {                   \
+                poly_exp2_x2(y2, e0, e1);                                                           \
+            } else {                                                                                \
+                float y0, y1;                                                                       \
+                unpack_f32x2(y2, y0, y1);                                                           \
+                e0 = fast_exp2(y0);                                                                 \
+                e1 = fast_exp2(y1);                                                                 \
+            }                                                                                       \
+            if (c & 1) sum_b = add_f32x2(sum_b, pack_f32x2(e0, e1));                                \
+            else sum_a = add_f32x2(sum_a, pack_f32x2(e0, e1));                                      \
+            pk[c] = pack_bf16(e0, e1);                                                              \
+        }                                                                                           \
+        tmem_st_32x16(s_tmem + (CH) * 16, pk);                                                      \
+    }
+    SCAIL_ATT_P_CHUNK(s0, 0)
+    SCAIL_ATT_P_CHUNK(s1, 1)
+    SCAIL_ATT_P_CHUNK(s2, 2)
+    SCAIL_ATT_P_CHUNK(s3, 3)
+#undef SCAIL_ATT_P_CHUNK
+    float la, lb, lc, ld;
+    unpack_f32x2(sum_a, la, lb);
+    unpack_f32x2(sum_b, lc, ld);
+    const float lsum = (la + lb) + (lc + ld);
+    l_run += lsum;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_pfull);
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -46,7 +132,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t k_smem = smem_base + 2 * ATT_TILE_BYTES;                // ATT_KV_STAGES tiles
     const uint32_t v_smem = k_smem + ATT_KV_STAGES * ATT_TILE_BYTES;       // ATT_KV_STAGES tiles
     const uint32_t bar_base = v_smem + ATT_KV_STAGES * ATT_TILE_BYTES;
-    enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 11, B_OFULL = 13, B_COUNT = 15 };
+    enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_PFULL = 11, B_OFULL = 13, B_PHALF = 15, B_COUNT = 17 };
     auto bar = [&](int i) { return bar_base + 8u * i; };
     const uint32_t tmem_slot = bar_base + 8u * B_COUNT;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -71,7 +157,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(B_SFULL + i), 1);
-            mbar_init(bar(B_PFULL + i), 128);
+            mbar_init(bar(B_PFULL + i), 4);  // one arrive per softmax warp
             mbar_init(bar(B_OFULL + i), 1);
         }
         fence_barrier_init();
@@ -85,6 +171,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    if (warp >= 8) setmaxnreg_dec<88>();
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -113,36 +200,52 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp runs the control flow (waits, descriptor arithmetic stay warp-uniform => uniform
+        // datapath); only the tcgen05 instructions themselves are issued by the elected lane.
+        {
+            const bool leader = elect_one_sync();
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
+            const uint64_t q_desc0 = umma_desc_kmajor_sw128(q_smem), q_desc1 = umma_desc_kmajor_sw128(q_smem + ATT_TILE_BYTES);
+            const uint64_t k_desc0 = umma_desc_kmajor_sw128(k_smem);
+            const uint64_t v_desc0 = umma_desc_mnmajor_sw128(v_smem, ATT_HALF_BYTES);
+            constexpr uint64_t STAGE_STEP = ATT_TILE_BYTES >> 4;  // descriptor address units are 16 B
             auto issue_qk = [&](int tile, int ks) {
+                if (p.debug == 5) return;
                 const uint32_t d = tmem_base + tile * 128;
+                const uint64_t qa = tile ? q_desc1 : q_desc0, kb = k_desc0 + ks * STAGE_STEP;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t off = (k >> 2) * ATT_HALF_BYTES + (k & 3) * 32;
-                    umma_ss<1>(d, umma_desc_kmajor_sw128(q_smem + tile * ATT_TILE_BYTES + off),
-                               umma_desc_kmajor_sw128(k_smem + ks * ATT_TILE_BYTES + off), idesc_qk, k != 0);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t off = ((k >> 2) * ATT_HALF_BYTES + (k & 3) * 32) >> 4;
+                        umma_ss<1>(d, qa + off, kb + off, idesc_qk, k != 0);
+                    }
                 }
             };
             auto issue_pv = [&](int tile, int vs, bool acc) {
+                if (p.debug == 6) return;
                 const uint32_t d = tmem_base + 256 + tile * 128;
                 const uint32_t a = tmem_base + tile * 128;  // P aliases S columns [0,64)
+                const uint64_t vb = v_desc0 + vs * STAGE_STEP;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    // 16 kv rows per step = 2048 B inside each 64-column half; halves are 16 KB apart (LBO)
-                    umma_ts(d, a + k * 8, umma_desc_mnmajor_sw128(v_smem + vs * ATT_TILE_BYTES + k * 2048, ATT_HALF_BYTES),
-                            idesc_pv, acc || k != 0);
+                    for (int k = 0; k < 8; ++k) {
+                        // 16 kv rows per step = 2048 B inside each 64-column half; halves are 16 KB apart (LBO)
+                        umma_ts(d, a + k * 8, vb + k * (2048 >> 4), idesc_pv, acc || k != 0);
+                    }
                 }
+            };
+            auto commit = [&](int b) {
+                if (leader) umma_commit(bar(b));
             };
             mbar_wait(bar(B_QFULL), 0, 20);
             mbar_wait(bar(B_KFULL + 0), 0, 21);
             tc_fence_after();
             issue_qk(0, 0);
-            umma_commit(bar(B_SFULL + 0));
+            commit(B_SFULL + 0);
             issue_qk(1, 0);
-            umma_commit(bar(B_SFULL + 1));
-            umma_commit(bar(B_KEMPTY + 0));
+            commit(B_SFULL + 1);
+            commit(B_KEMPTY + 0);
             for (int j = 0; j < n_kv; ++j) {
                 const int vs = j % ATT_KV_STAGES;
                 const uint32_t vph = (j / ATT_KV_STAGES) & 1;
@@ -150,32 +253,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const int ks = (j + 1) % ATT_KV_STAGES;
                 const uint32_t kph = ((j + 1) / ATT_KV_STAGES) & 1;
                 mbar_wait(bar(B_VFULL + vs), vph, 22);
-                mbar_wait(bar(B_PFULL + 0), j & 1, 23);
+                const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && leader;
+                if (tr) p.trace[j * 8 + 0] = clock64();
+                if (p.debug != 2) mbar_wait(bar(B_PFULL + 0), j & 1, 23);
+                if (tr) p.trace[j * 8 + 1] = clock64();
                 tc_fence_after();
                 issue_pv(0, vs, j > 0);
                 if (more) {
                     mbar_wait(bar(B_KFULL + ks), kph, 24);
                     tc_fence_after();
                     issue_qk(0, ks);
-                    umma_commit(bar(B_SFULL + 0));
+                    commit(B_SFULL + 0);
+                    if (tr) p.trace[j * 8 + 2] = clock64();
                 } else {
-                    umma_commit(bar(B_OFULL + 0));
+                    commit(B_OFULL + 0);
                 }
-                mbar_wait(bar(B_PFULL + 1), j & 1, 25);
+                if (p.debug != 2) mbar_wait(bar(B_PFULL + 1), j & 1, 25);
+                if (tr) p.trace[j * 8 + 3] = clock64();
                 tc_fence_after();
                 issue_pv(1, vs, j > 0);
-                umma_commit(bar(B_VEMPTY + vs));
+                commit(B_VEMPTY + vs);
                 if (more) {
                     issue_qk(1, ks);
-                    umma_commit(bar(B_SFULL + 1));
-                    umma_commit(bar(B_KEMPTY + ks));
+                    commit(B_SFULL + 1);
+                    commit(B_KEMPTY + ks);
                 } else {
-                    umma_commit(bar(B_OFULL + 1));
+                    commit(B_OFULL + 1);
                 }
             }
         }
-    } else {
+    } else if (warp < 8) {
         // ===================== softmax warpgroups (+ O rescale + epilogue) =====================
+        setmaxnreg_inc<208>();
         const int tile = warp >> 2;  // 0 or 1
         const int sub = warp & 3;
         const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
@@ -184,70 +293,35 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         float m_run = -INFINITY;  // running max, already multiplied by scale_log2
         float l_run = 0.f;
         for (int j = 0; j < n_kv; ++j) {
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
+            if (tr) p.trace[j * 8 + 4] = clock64();
             mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
+            if (tr) p.trace[j * 8 + 5] = clock64();
             tc_fence_after();
-            uint32_t s0[32], s1[32], s2[32], s3[32];
-            tmem_ld_32x32(s_tmem + 0, s0);
-            tmem_ld_32x32(s_tmem + 32, s1);
-            tmem_ld_32x32(s_tmem + 64, s2);
-            tmem_ld_32x32(s_tmem + 96, s3);
-            tmem_ld_wait();
             const int valid = p.kv_len - j * ATT_BKV;  // >= 128 except on the last tile
-            if (valid < ATT_BKV) {
+            if (p.debug == 3) {  // TMEM read only
+                uint32_t t0[32], t1[32], t2[32], t3[32];
+                tmem_ld_32x32(s_tmem + 0, t0);
+                tmem_ld_32x32(s_tmem + 32, t1);
+                tmem_ld_32x32(s_tmem + 64, t2);
+                tmem_ld_32x32(s_tmem + 96, t3);
+                tmem_ld_wait();
+                uint32_t x = 0;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if (c >= valid) s0[c] = 0xff800000u;
-                    if (c + 32 >= valid) s1[c] = 0xff800000u;
-                    if (c + 64 >= valid) s2[c] = 0xff800000u;
-                    if (c + 96 >= valid) s3[c] = 0xff800000u;
-                }
+                for (int c = 0; c < 32; ++c) x ^= t0[c] ^ t1[c] ^ t2[c] ^ t3[c];
+                if (x == 0x12345678u) l_run += 1.f;
             }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[c]), __uint_as_float(s1[c])),
-                                     fmaxf(__uint_as_float(s2[c]), __uint_as_float(s3[c]))));
+            if (p.debug == 1 || p.debug == 3 || p.debug >= 5) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_PFULL + tile));
+                l_run = 1.f;
+                continue;
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
-            if (__any_sync(0xffffffffu, need)) {
-                const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
-                m_run = m_new;
-                l_run *= alpha;
-                if (j > 0) {
-#pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld_32x32(o_tmem + c * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-                        tmem_st_32x32(o_tmem + c * 32, o);
-                    }
-                }
-            }
-            float lsum = 0.f;
-            const float neg_m = -m_run;
-#define SCAIL_ATT_P_CHUNK(SRC, CH)                                                                      \
-            {                                                                                           \
-                uint32_t pk[16];                                                                        \
-                _Pragma("unroll") for (int c = 0; c < 16; ++c) {                                        \
-                    const float e0 = fast_exp2(fmaf(__uint_as_float(SRC[2 * c]), p.scale_log2, neg_m)); \
-                    const float e1 = fast_exp2(fmaf(__uint_as_float(SRC[2 * c + 1]), p.scale_log2, neg_m)); \
-                    lsum += e0 + e1;                                                                    \
-                    pk[c] = pack_bf16(e0, e1);                                                          \
-                }                                                                                       \
-                tmem_st_32x16(s_tmem + (CH) * 16, pk);                                                  \
-            }
-            SCAIL_ATT_P_CHUNK(s0, 0)
-            SCAIL_ATT_P_CHUNK(s1, 1)
-            SCAIL_ATT_P_CHUNK(s2, 2)
-            SCAIL_ATT_P_CHUNK(s3, 3)
-#undef SCAIL_ATT_P_CHUNK
-            l_run += lsum;
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(bar(B_PFULL + tile));
+            if (valid < ATT_BKV)  // warp-uniform; a separate instantiation keeps the 128 compare/selects off the hot path
+                softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
+            else
+                softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
         }
         // ---- epilogue: O / l -> bf16 -> global ----
         mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);

@@ -122,7 +122,8 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp runs the warp-uniform control flow; the elected lane issues tcgen05.mma / commit
+            const bool leader = elect_one_sync();
             constexpr uint32_t idesc = umma_idesc_bf16(CONV_BM, BN, 0, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -136,12 +137,14 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + CONV_A_BYTES);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < CONV_BK / 16; ++k) umma_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(empty_bar(stage));
+                        for (int k = 0; k < CONV_BK / 16; ++k) umma_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit(empty_bar(stage));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));
+                if (leader) umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -124,8 +124,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer =====================
+        // whole warp runs the (warp-uniform) control flow; the elected lane issues tcgen05.mma / commit
+        {
+            const bool leader = elect_one_sync();
             constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -141,15 +143,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
                     const uint64_t da = umma_desc_kmajor_sw128(sa);
                     const uint64_t db = umma_desc_kmajor_sw128(sa + GEMM_A_BYTES);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        // +32 B per K=16 step inside the 128-B swizzle atom (descriptor units of 16 B)
-                        umma_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            // +32 B per K=16 step inside the 128-B swizzle atom (descriptor units of 16 B)
+                            umma_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs have read it
                     if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (leader) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -14,6 +14,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_idx() { return threadIdx.x & 31; }
 
+// One lane of the (converged) warp is elected; ptxas keeps operands of code guarded by this predicate in
+// uniform registers (no R2UR round trips), which matters for the single-thread tcgen05.mma issue rate.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -48,9 +56,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");  // suspend-time hint: sleep in HW, not spin
     return done != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) after ~4 s instead of a hung GPU.
@@ -262,6 +270,50 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// ---- packed f32x2 math (Blackwell FFMA2 / FADD2): two fp32 lanes per 64-bit register
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel err 7.5e-5):
+// relieves the MUFU pipe, which is co-critical with the tensor pipe in attention (16 ex2/clk/SM).
+__device__ __forceinline__ void poly_exp2_x2(uint64_t y2, float& e0, float& e1) {
+    float y0, y1;
+    unpack_f32x2(y2, y0, y1);
+    y2 = pack_f32x2(fmaxf(y0, -125.0f), fmaxf(y1, -125.0f));
+    const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+    const uint64_t t2 = add_f32x2(y2, magic);                                       // round-to-nearest integer in the mantissa
+    const uint64_t negn = fma_f32x2(t2, pack_f32x2(-1.0f, -1.0f), magic);          // -(round(y))
+    const uint64_t f2 = add_f32x2(y2, negn);                                        // y - round(y) in [-0.5, 0.5]
+    uint64_t p2 = fma_f32x2(pack_f32x2(0.05517083778977394f, 0.05517083778977394f), f2,
+                            pack_f32x2(0.24260935187339783f, 0.24260935187339783f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999281764030457f, 0.9999281764030457f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));         // scale by 2^round(y)
+    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ float fast_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
