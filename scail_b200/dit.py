@@ -128,6 +128,8 @@ class _Workspace:
         self.bufs = {}
 
     def get(self, name, shape, device, dtype=torch.bfloat16):
+        # one buffer set per CUDA stream: the context-parallel path runs the two CFG branches on two streams
+        name = (name, torch.cuda.current_stream(device).cuda_stream)
         key = (name, tuple(shape), str(device), dtype)
         b = self.bufs.get(key)
         if b is None:
@@ -504,10 +506,26 @@ class DiffusionTransformer(nn.Module):
         hidden = self.mixins["patch_embed"].word_embedding_forward(None, images=xb, ref_concat=ref,
                                                                    concat_smpl_render=pose, _hidden_out=hidden)
         cp = self.mixins["adaln_layer"].cp
-        if cp is not None and cp.size > 1:
-            hidden = cp.shard_tokens(hidden)
+        ad = self.mixins["adaln_layer"]
+        if cp is None or cp.size == 1:
+            for l in range(self.num_layers):
+                hidden = ad.layer_forward(hidden, None, layer_id=l, **kw)
+            return self.mixins["final_layer"].final_forward(hidden, **kw)
+        # ---- context parallel: token shard; the CFG branches (independent batch elements) run on separate
+        # streams so that one branch's K/V all-gather overlaps the other branch's GEMMs / attention ----
+        local = cp.shard_tokens(hidden)
+        main = torch.cuda.current_stream()
+        streams = cp.branch_streams(b, x.device)
+        per = []
+        for i in range(b):
+            kwi = dict(kw, emb=adaln[i:i + 1], encoder_outputs=text[i:i + 1], image_clip_features=clip[i:i + 1])
+            per.append([local[i:i + 1].contiguous(), kwi])
+            streams[i].wait_stream(main)
         for l in range(self.num_layers):
-            hidden = self.mixins["adaln_layer"].layer_forward(hidden, None, layer_id=l, **kw)
-        if cp is not None and cp.size > 1:
-            hidden = cp.gather_tokens(hidden, N)
+            for i in range(b):
+                with torch.cuda.stream(streams[i]):
+                    per[i][0] = ad.layer_forward(per[i][0], None, layer_id=l, **per[i][1])
+        for i in range(b):
+            main.wait_stream(streams[i])
+        hidden = cp.gather_tokens(torch.cat([h for h, _ in per], 0), N)
         return self.mixins["final_layer"].final_forward(hidden, **kw)

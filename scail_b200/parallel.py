@@ -20,6 +20,14 @@ class ContextParallel:
         self.size = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self._kv = {}
+        self._q = {}
+        self._streams = {}
+
+    def branch_streams(self, n, device):
+        key = (n, str(device))
+        if key not in self._streams:
+            self._streams[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        return self._streams[key]
 
     # ---- token sharding (kernel-free: also exercised on CPU/gloo by tests/test_parallel_cpu.py) ----
     def local_len(self, n_total):
@@ -46,9 +54,10 @@ class ContextParallel:
     def kv_buffer(self, B, n_local, d, device, dtype=torch.bfloat16):
         """[B, P, N/P, 2d]: batch-major so that, after the gather, batch b's keys/values are the contiguous
         [P*N/P, 2d] matrix the attention kernel addresses with kv_batch_rows = N."""
-        key = (B, n_local, d, str(device), dtype)
+        sid = torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
+        key = (B, n_local, d, str(device), dtype, sid)  # one buffer per stream (CFG branches run concurrently)
         if key not in self._kv:
-            self._kv = {key: torch.empty(B, self.size, n_local, 2 * d, device=device, dtype=dtype)}
+            self._kv[key] = torch.empty(B, self.size, n_local, 2 * d, device=device, dtype=dtype)
         return self._kv[key]
 
     def gather_kv(self, kvbuf, async_op=True):
@@ -73,9 +82,10 @@ class ContextParallel:
             ops.gemm(h2[b * n_local:(b + 1) * n_local], w[d:], bias[d:], out=slot)
             ops.rmsnorm_rope(slot, n_local, d, [(0, wk)], cos_l, sin_l, eps=eps)
         works = self.gather_kv(kvbuf, async_op=True)
-        q = torch.empty(B * n_local, d, device=dev, dtype=torch.bfloat16) if not hasattr(self, "_q") or \
-            self._q.shape != (B * n_local, d) or self._q.device != dev else self._q
-        self._q = q
+        qkey = (B * n_local, d, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        if qkey not in self._q:
+            self._q[qkey] = torch.empty(B * n_local, d, device=dev, dtype=torch.bfloat16)
+        q = self._q[qkey]
         ops.gemm(h2, w[:d], bias[:d], out=q)  # overlaps the all-gather
         ops.rmsnorm_rope(q, n_local, d, [(0, wq)], cos_l, sin_l, eps=eps)
         for wk_ in works:
