@@ -183,8 +183,8 @@ def run_reference_arm(args):
 
 
 def workload_config(n_gpus):
-    return {"workload": "SCAIL-14B one sampler step (CFG batch-2 DiT forward + CFG + Euler), latent 21x64x64 "
-                        "(512x512, 81 frames), N=27904 tokens (ref 1024 | noise 21504 | pose 5376), 40 blocks, "
+    return {"workload": f"SCAIL-14B one sampler step (CFG batch-2 DiT forward + CFG + Euler), latent {T_LAT}x{H_LAT}x{W_LAT} "
+                        f"({8 * H_LAT}x{8 * W_LAT}, {4 * (T_LAT - 1) + 1} frames), N={seq_len()} tokens (ref | noise | pose), 40 blocks, "
                         "d=5120, 40 heads x 128, MLP 13824, text 512 + CLIP 257 keys",
             "global_batch": 2, "seq_len": seq_len(), "parallelism": f"cp{n_gpus}" if n_gpus > 1 else "single",
             "l2_policy": "inputs larger than L2 (32 GB weights, >5 GB activations per step)"}
@@ -198,7 +198,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)  # debugging only; default = full model
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--latent", default=None, help="TxHxW latent override, e.g. 21x64x112 (the reference's default 512x896); "
+                    "the default 21x64x64 is the BASELINE.json config")
     args = ap.parse_args()
+    if args.latent:
+        global T_LAT, H_LAT, W_LAT
+        T_LAT, H_LAT, W_LAT = (int(v) for v in args.latent.lower().split("x"))
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -274,7 +279,10 @@ def main():
     peaks, peak_src = measured_peaks()
     n = seq_len()
     step_flops = 2 * forward_flops(n) * args.layers / LAYERS
-    attn_flops = 4 * 2 * HEADS * (n / world) * n * 128  # per self-attention launch on one rank (b=2)
+    # self-attention work of one rank per step = 40 layers x 4*B*H*(N/P)*N*128; at N>1 the two CFG branches are
+    # separate launches (80 per step), so the per-launch figures are derived from the per-step totals
+    n_attn = len(attn_ms) // args.steps if attn_ms else 0
+    attn_flops = (4 * 2 * HEADS * (n / world) * n * 128) * args.layers / max(n_attn, 1)
     attn_avg = statistics.mean(attn_ms) if attn_ms else None
     value = 1000.0 / ms
     out = {"metric": "denoising steps/sec (SCAIL-14B, 512p/81f)", "value": value, "unit": "steps/s", "n_gpus": world,
@@ -287,7 +295,7 @@ def main():
            "gpu_launches": launches, "clocks": clk,
            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": hs.h2d_bytes,
                    "d2h_bytes_per_step": hs.d2h_bytes},
-           "roofline": {"kernel": "attention_fwd_kernel (self-attention, 40 launches/step)", "bound": "tensor",
+           "roofline": {"kernel": f"attention_fwd_kernel (self-attention, {n_attn} launches/step)", "bound": "tensor",
                         "achieved": attn_flops / attn_avg / 1e9 if attn_avg else None,
                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": attn_flops / attn_avg / 1e9 / peaks["bf16_tflops_sustained"] if attn_avg else None,

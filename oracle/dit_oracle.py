@@ -112,15 +112,16 @@ def unpatchify(x, ref_len, seq_len, T, H, W, c=16, patch=(1, 2, 2)):
 def timestep_embedding(timesteps, dim, max_period=10000):
     """sgm/modules/diffusionmodules/util.py:207-231 (freqs fp64 -> args fp32)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float64) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float64, device=timesteps.device) / half)
     args = timesteps[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], -1).float()
 
 
 def rmsnorm(x, w, eps=1e-6):
-    """dit_video_crossattn_sc_xc.py:61-68."""
+    """dit_video_crossattn_sc_xc.py:61-68 (fp32 math, weight multiply in fp32, one cast back)."""
+    dt = x.dtype
     x = x.float()
-    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+    return (w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))).to(dt)
 
 
 def layernorm(x, w=None, b=None, eps=1e-6):
@@ -163,6 +164,8 @@ def merge_heads(x):
 
 def sdpa(q, k, v):
     """sat/transformer_defaults.py:67-72 (non-causal, scale 1/sqrt(d), no mask)."""
+    if q.dtype != torch.float32:  # "reference as shipped" mode: the library SDPA the reference calls
+        return F.scaled_dot_product_attention(q, k, v)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     return torch.softmax(s, -1) @ v
 
@@ -223,38 +226,43 @@ def final_layer(sd, x, emb):
     return linear(sd, "mixins.final_layer.linear", modulate(layernorm(x), shift, scale))
 
 
-def embeddings(sd, timesteps, context, clip_feats, time_freq_dim=256):
+def embeddings(sd, timesteps, context, clip_feats, time_freq_dim=256, dtype=torch.float32):
     """DiffusionTransformer.forward, dit_video_crossattn_sc_xc.py:1505-1555."""
     text = linear(sd, "text_embedding.2", F.gelu(linear(sd, "text_embedding.0", context), approximate="tanh"))
     c = layernorm(clip_feats, sd["clip_proj.proj.0.weight"], sd["clip_proj.proj.0.bias"], eps=1e-5)
     c = linear(sd, "clip_proj.proj.3", F.gelu(linear(sd, "clip_proj.proj.1", c)))
     clip = layernorm(c, sd["clip_proj.proj.4.weight"], sd["clip_proj.proj.4.bias"], eps=1e-5)
-    emb = linear(sd, "time_embed.2", F.silu(linear(sd, "time_embed.0", timestep_embedding(timesteps, time_freq_dim))))
+    t_emb = timestep_embedding(timesteps, time_freq_dim).to(device=context.device, dtype=dtype)
+    emb = linear(sd, "time_embed.2", F.silu(linear(sd, "time_embed.0", t_emb)))
     adaln = linear(sd, "adaln_projection.1", F.silu(emb))
     return text, clip, emb, adaln
 
 
 def dit_forward(sd, x, timesteps, context, ref_concat, concat_smpl_render, image_clip_features,
-                n_heads, n_layers, max_frames=21, max_h=150, max_w=150, return_hidden=False):
+                n_heads, n_layers, max_frames=21, max_h=150, max_w=150, return_hidden=False, dtype=torch.float32):
     """DiffusionTransformer.forward (dit_video_crossattn_sc_xc.py:1452-1587) ->
     BaseTransformer.forward (sat/model/transformer.py:572-746), fp32, CPU.
     x [b,t,16,h,w]; ref_concat [1|b,1,16,h,w]; concat_smpl_render [1|b,t,16,h/2,w/2];
     context [b,L,text_dim]; image_clip_features [1|b,257,1280]; timesteps [b]."""
-    sd = {k: v.float() for k, v in sd.items()}
+    # dtype=torch.bfloat16 runs the same op chain in bf16 (rounding after every op, like the reference as shipped:
+    # SURVEY §3.5) — used only to put "reference-style bf16" error next to ours in the GPU parity tests
+    sd = {k: v.to(dtype) for k, v in sd.items()}
     b, t, _, h, w = x.shape
-    x = x.float()
+    x = x.to(dtype)
+    dev = x.device
 
     def rep(a):
-        return a.float().repeat(b // a.shape[0], *([1] * (a.dim() - 1)))
+        return a.to(dtype).repeat(b // a.shape[0], *([1] * (a.dim() - 1)))
 
-    images = torch.cat([x, torch.zeros(b, t, 4, h, w)], 2)  # :1468,1503
-    ref = torch.cat([rep(ref_concat), torch.ones(b, 1, 4, h, w)], 2)  # :1483-1486
-    pose = torch.cat([rep(concat_smpl_render), torch.ones(b, t, 4, h // 2, w // 2)], 2)  # :1496-1501
-    text, clip, emb, adaln = embeddings(sd, timesteps, context.float(), rep(image_clip_features))
+    images = torch.cat([x, torch.zeros(b, t, 4, h, w, dtype=dtype, device=dev)], 2)  # :1468,1503
+    ref = torch.cat([rep(ref_concat), torch.ones(b, 1, 4, h, w, dtype=dtype, device=dev)], 2)  # :1483-1486
+    pose = torch.cat([rep(concat_smpl_render), torch.ones(b, t, 4, h // 2, w // 2, dtype=dtype, device=dev)], 2)  # :1496-1501
+    text, clip, emb, adaln = embeddings(sd, timesteps, context.to(dtype), rep(image_clip_features), dtype=dtype)
     ref_len, seq_len, pose_len = segment_lengths(t, h, w)
     T, H, W = t, h // 2, w // 2
     d = sd["mixins.final_layer.linear.weight"].shape[1]
     cos, sin = rope_tables(d // n_heads, T, H, W, max_frames, max_h, max_w)
+    cos, sin = cos.to(device=dev, dtype=dtype), sin.to(device=dev, dtype=dtype)  # :553-554 `.to(t.dtype)`
     hid = patch_embed(sd, images, ref, pose)
     hiddens = [hid]
     for l in range(n_layers):
