@@ -24,7 +24,7 @@ constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: one 128x128 bf16 tile (two 64-column halves)
 constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
 constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle warps}
-constexpr int ATT_POLY_EVERY = 4;  // every 4th column pair takes the FMA-pipe exp2 (0 = never)
+constexpr int ATT_POLY_EVERY = 0;  // every 4th column pair takes the FMA-pipe exp2 (0 = never)
 constexpr int ATT_SMEM_BYTES = (2 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 
 struct AttnParams {
