@@ -202,6 +202,19 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const scail
 }
 
 
+template <int LP, int VPL>
+static int launch_rmsnorm_cl(const void* x, const void* gamma, void* out, int64_t npix, int C, int silu, cudaStream_t st) {
+    const int pix_per_block = 8 * (32 / LP);
+    const int grid = blocks_for(npix, pix_per_block);
+    auto xp = static_cast<const __nv_bfloat16*>(x);
+    auto gp = static_cast<const __nv_bfloat16*>(gamma);
+    auto op = static_cast<__nv_bfloat16*>(out);
+    if (silu) scail::rmsnorm_cl_kernel<true, LP, VPL><<<grid, 256, 0, st>>>(xp, gp, op, npix, C);
+    else scail::rmsnorm_cl_kernel<false, LP, VPL><<<grid, 256, 0, st>>>(xp, gp, op, npix, C);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -421,15 +434,19 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
 
 int scail_rmsnorm_cl(const void* x, const void* gamma, void* out, int64_t npix, int64_t C, int silu, scail_stream_t stream) {
     SCAIL_REQUIRE(x && gamma && out, "rmsnorm_cl: null operand");
-    SCAIL_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8192, "rmsnorm_cl: C must be a multiple of 8");
-    const int G = (int)C / 8, ppb = 1024 / G;
-    SCAIL_REQUIRE(ppb >= 1, "rmsnorm_cl: C too large");
-    const int grid = blocks_for(npix, ppb);
     auto st = static_cast<cudaStream_t>(stream);
-    if (silu) scail::rmsnorm_cl_kernel<true><<<grid, 256, ppb * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(out), npix, (int)C);
-    else scail::rmsnorm_cl_kernel<false><<<grid, 256, ppb * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma), static_cast<__nv_bfloat16*>(out), npix, (int)C);
-    SCAIL_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    switch (C) {  // C = 8 * LP * VPL
+        case 16:  return launch_rmsnorm_cl<2, 1>(x, gamma, out, npix, 16, silu, st);
+        case 32:  return launch_rmsnorm_cl<4, 1>(x, gamma, out, npix, 32, silu, st);
+        case 64:  return launch_rmsnorm_cl<8, 1>(x, gamma, out, npix, 64, silu, st);
+        case 96:  return launch_rmsnorm_cl<4, 3>(x, gamma, out, npix, 96, silu, st);
+        case 128: return launch_rmsnorm_cl<16, 1>(x, gamma, out, npix, 128, silu, st);
+        case 192: return launch_rmsnorm_cl<8, 3>(x, gamma, out, npix, 192, silu, st);
+        case 256: return launch_rmsnorm_cl<16, 2>(x, gamma, out, npix, 256, silu, st);
+        case 384: return launch_rmsnorm_cl<16, 3>(x, gamma, out, npix, 384, silu, st);
+        case 512: return launch_rmsnorm_cl<16, 4>(x, gamma, out, npix, 512, silu, st);
+        default:  return fail(-1, "rmsnorm_cl: unsupported channel count %lld (supported: 16,32,64,96,128,192,256,384,512)", (long long)C);
+    }
 }
 
 int scail_upsample2x_cl(const void* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, scail_stream_t stream) {

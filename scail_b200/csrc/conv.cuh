@@ -247,59 +247,53 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 // ------------------------------------------------------------------ VAE elementwise kernels (channels-last)
 
 // RMS_norm over channels (F.normalize(x, dim=C) * sqrt(C) * gamma, wan_vae.py:39-54) followed by SiLU.
-// x, out: [npix, C] bf16; C % 8 == 0.  Each block handles PIX pixels; partial sums go through shared memory.
-template <bool SILU>
-__global__ void __launch_bounds__(256) rmsnorm_cl_kernel(const __nv_bfloat16* x, const __nv_bfloat16* gamma,
-                                                         __nv_bfloat16* out, int64_t npix, int C) {
-    extern __shared__ float ssq[];  // [pix_per_block]
-    const int G = C >> 3;                 // uint4 vectors per pixel
-    const int pix_per_block = 1024 / G;   // <= 1024 vectors per block iteration (4 per thread)
-    const int64_t pix0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
-    const int64_t rem = npix - pix0;
-    const int nvec = static_cast<int>(rem < pix_per_block ? rem : pix_per_block) * G;
-    for (int i = threadIdx.x; i < pix_per_block; i += blockDim.x) ssq[i] = 0.f;
-    __syncthreads();
-    const uint4* xin = reinterpret_cast<const uint4*>(x + pix0 * C);
-    uint4 v[4];
+// x, out: [npix, C] bf16, C = 8 * LP * VPL.  LP lanes (a power of two) share one pixel, each holding VPL 16-byte
+// vectors; the sum of squares is reduced with xor-shuffles inside the LP-lane group — no shared memory, no
+// block barrier, fully coalesced 16-byte accesses (a warp covers 32/LP consecutive pixels).
+template <bool SILU, int LP, int VPL>
+__global__ void __launch_bounds__(256) rmsnorm_cl_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                                         __nv_bfloat16* __restrict__ out, int64_t npix, int C) {
+    constexpr int G = LP * VPL;  // vectors per pixel
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LP;   // lane within the pixel group
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t pix = warp * (32 / LP) + lane / LP;
+    const bool ok = pix < npix;
+    const uint4* xin = reinterpret_cast<const uint4*>(x) + pix * G;
+    uint4 v[VPL];
+    float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < nvec) {
-            v[k] = xin[i];
-            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-            float s = 0.f;
+    for (int k = 0; k < VPL; ++k) {
+        v[k] = ok ? xin[k * LP + sub] : make_uint4(0, 0, 0, 0);
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_bf16(w[j]);
-                s += f.x * f.x + f.y * f.y;
-            }
-            atomicAdd(&ssq[i / G], s);
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16(w[j]);
+            ss += f.x * f.x + f.y * f.y;
         }
     }
-    __syncthreads();
-    const float sqrtc = sqrtf(static_cast<float>(C));
-    uint4* o = reinterpret_cast<uint4*>(out + pix0 * C);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = threadIdx.x + k * 256;
-        if (i < nvec) {
-            const float inv = sqrtc / fmaxf(sqrtf(ssq[i / G]), 1e-12f);
-            const int c0 = (i % G) * 8;
-            uint4 g = *reinterpret_cast<const uint4*>(gamma + c0);
-            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, gw[4] = {g.x, g.y, g.z, g.w};
-            uint32_t r[4];
+    for (int o = LP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (!ok) return;
+    const float inv = sqrtf(static_cast<float>(C)) / fmaxf(sqrtf(ss), 1e-12f);
+    uint4* o4 = reinterpret_cast<uint4*>(out) + pix * G;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_bf16(w[j]), g2 = unpack_bf16(gw[j]);
-                float a = f.x * inv * g2.x, b = f.y * inv * g2.y;
-                if (SILU) {
-                    a = a / (1.0f + __expf(-a));
-                    b = b / (1.0f + __expf(-b));
-                }
-                r[j] = pack_bf16(a, b);
+    for (int k = 0; k < VPL; ++k) {
+        const int vi = k * LP + sub;
+        uint4 g = *reinterpret_cast<const uint4*>(gamma + vi * 8);
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w}, gw[4] = {g.x, g.y, g.z, g.w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16(w[j]), g2 = unpack_bf16(gw[j]);
+            float a = f.x * inv * g2.x, b = f.y * inv * g2.y;
+            if (SILU) {
+                a = a / (1.0f + __expf(-a));
+                b = b / (1.0f + __expf(-b));
             }
-            o[i] = make_uint4(r[0], r[1], r[2], r[3]);
+            r[j] = pack_bf16(a, b);
         }
+        o4[vi] = make_uint4(r[0], r[1], r[2], r[3]);
     }
 }
 

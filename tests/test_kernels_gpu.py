@@ -206,3 +206,27 @@ def test_patchify_unpatchify_index_exact():
     lin = code[n_ref:n_ref + n_seq].to(torch.bfloat16).cuda().contiguous()[None]
     got = ops.unpatchify(lin, 1, t, h // 2, w // 2).float().cpu()
     assert torch.equal(got, (ix["unpatchify"] % 251).float())
+
+
+def test_error_paths_return_codes_not_crashes():
+    """Bad arguments must come back as a negative return code + message (never exit / crash / silent fallback)."""
+    from scail_b200 import _lib, ops
+    a, w = rnd(16, 24), rnd(8, 24)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(a[:, :20].contiguous(), w[:, :20].contiguous())  # K = 20
+    with pytest.raises(RuntimeError, match="unknown epilogue"):
+        ops.gemm(a, w, epilogue=17)
+    with pytest.raises(RuntimeError, match="gate/residual required"):
+        ops.gemm(a, w, epilogue=ops.EPI_BIAS_GATE_RES)
+    x = rnd(2, 4, 384)
+    with pytest.raises(RuntimeError, match="multiple of 256"):
+        ops.ln_modulate(x)
+    with pytest.raises(RuntimeError, match="unsupported channel count"):
+        ops.rmsnorm_cl(rnd(4, 40), rnd(40))
+    h = _lib.lib()
+    assert h.scail_attention(None, 0, None, 0, None, 0, None, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, 0, None) < 0
+    assert b"null operand" in h.scail_last_error()
+    # the library is still healthy afterwards
+    out = ops.gemm(rnd(128, 64), rnd(256, 64))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
