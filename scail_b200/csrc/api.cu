@@ -115,21 +115,22 @@ int make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uin
 // 4-D bf16 channels-last activation [T, H, W, C]: dims (C, W, H, T), box (64, 16, 8, 1), SWIZZLE_128B.
 // Out-of-bounds box elements (channel tail, spatial halo, t < 0) are zero-filled.
 struct Map4Key {
-    const void* ptr; uint64_t T, H, W, C;
-    bool operator==(const Map4Key& o) const { return ptr == o.ptr && T == o.T && H == o.H && W == o.W && C == o.C; }
+    const void* ptr; uint64_t T, H, W, C; uint32_t bw, bh;
+    bool operator==(const Map4Key& o) const { return ptr == o.ptr && T == o.T && H == o.H && W == o.W && C == o.C && bw == o.bw && bh == o.bh; }
 };
 struct Map4KeyHash {
     size_t operator()(const Map4Key& k) const {
         size_t h = reinterpret_cast<size_t>(k.ptr);
         auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.T); mix(k.H); mix(k.W); mix(k.C);
+        mix(k.T); mix(k.H); mix(k.W); mix(k.C); mix(k.bw); mix(k.bh);
         return h;
     }
 };
 std::unordered_map<Map4Key, CUtensorMap, Map4KeyHash> g_maps4;
 
-int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t C, CUtensorMap* out) {
-    Map4Key key{ptr, T, H, W, C};
+int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t C, CUtensorMap* out, uint32_t box_w = 16,
+                   uint32_t box_h = 8) {
+    Map4Key key{ptr, T, H, W, C, box_w, box_h};
     {
         std::lock_guard<std::mutex> lk(g_map_mu);
         auto it = g_maps4.find(key);
@@ -140,7 +141,7 @@ int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C % 8)) return fail(-1, "conv input must be 16-byte aligned with C %% 8 == 0");
     cuuint64_t gdim[4] = {C, W, H, T};
     cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
-    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t box[4] = {64, box_w, box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
@@ -427,6 +428,21 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
     p.out = out; p.ldo = ldo; p.ldr = ldr; p.ocols = (int)(ocols > 0 ? ocols : Cout); p.fmul = fmul > 0 ? fmul : 1;
     p.epilogue = epilogue;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool row_ok_env = !(getenv("SCAIL_CONV_ROW") && atoi(getenv("SCAIL_CONV_ROW")) == 0);
+    if (row_ok_env && KH == 3 && KW == 3 && W >= 128 && Cout % 96 == 0 && epilogue != CONV_EPI_HEAD_CLAMP && fmul <= 1 &&
+        (ocols <= 0 || ocols == Cout)) {
+        // row-tile kernel: 2 output rows x 128 pixels x 96 channels per iteration, taps as shifted smem views
+        CUtensorMap txr, twr;
+        if ((rc = make_tmap_cl4d(x, T, H, W, Cin, &txr, CROW_A_ROWS, 2))) return rc;
+        if ((rc = make_tmap_2d(w2, Cout, (uint64_t)taps * Cin, (uint64_t)taps * Cin, CROW_BN, 64, &twr))) return rc;
+        if ((rc = set_smem(conv3d_row_kernel, CROW_SMEM_BYTES))) return rc;
+        const int tiles = (int)(T * ((H + 1) / 2) * blocks_for(W, CROW_PW) * blocks_for(Cout, CROW_BN));
+        const int sms = sm_count();
+        SCAIL_REQUIRE(sms > 0, "conv3d: no CUDA device");
+        conv3d_row_kernel<<<tiles < sms ? tiles : sms, CONV_THREADS, CROW_SMEM_BYTES, st>>>(txr, twr, p);
+        SCAIL_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (BN == 16) return launch_conv<16>(tx, tw, p, st);
     if (BN == 96) return launch_conv<96>(tx, tw, p, st);
     return launch_conv<192>(tx, tw, p, st);

@@ -244,6 +244,208 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ row-tile variant (3x3 spatial taps, W >= 128)
+// The generic kernel above re-fetches the input patch from L2 for each of the 27 taps and the weight slice for every
+// 128-pixel tile; with 96 output channels that is ~146 B/clk/SM of L2->SM traffic and the kernel is L2-bound.
+// Here one CTA iteration produces TWO output rows (h0, h0+1) x 128 pixels x 96 channels.  Per (dt, dh, 64-channel
+// slice) ONE TMA box [2 rows x 130 pixels x 64 ch] is staged (input rows h0+dh-1, h0+dh with a one-pixel halo on both
+// sides); the three dw taps of both output rows are row-shifted views of it: the UMMA descriptor start address is
+// simply advanced by whole 128-byte rows (measured on B200: the 128B swizzle is a function of the absolute shared
+// memory address, exactly as TMA wrote it, so no descriptor base_offset is needed), and the three weight slices
+// of the stage are shared by both rows: 70 KB feed 24 UMMAs (1152 cycles) = 62 B/clk/SM.
+constexpr int CROW_PW = 128, CROW_BN = 96, CROW_STAGES = 3;
+constexpr int CROW_A_ROWS = CROW_PW + 2;                                       // 130 pixels per input row
+constexpr int CROW_A_BYTES = ((2 * CROW_A_ROWS * 128 + 1023) / 1024) * 1024;   // 33280 -> 33792
+constexpr int CROW_B_BYTES = CROW_BN * CONV_BK * 2;                            // 12288 per dw tap
+constexpr int CROW_STAGE_BYTES = CROW_A_BYTES + 3 * CROW_B_BYTES;              // 70656
+constexpr int CROW_SMEM_BYTES = CROW_STAGES * CROW_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t CROW_TX_BYTES = 2 * CROW_A_ROWS * 128 + 3 * CROW_B_BYTES;   // bytes the TMA engine reports per stage
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+    constexpr int BN = CROW_BN, STAGES = CROW_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * CROW_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_h = (p.H + 1) / 2, tiles_w = (p.W + CROW_PW - 1) / CROW_PW;
+    const int num_m = p.T * tiles_h * tiles_w;
+    const int num_n = (p.Cout + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int kc_per_tap = (p.Cin + CONV_BK - 1) / CONV_BK;
+    const int num_k = p.KT * 3 * kc_per_tap;  // stages per tile: (dt, dh, kc)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    auto tile_coords = [&](int tile, int& t, int& h0, int& w0, int& n_blk) {
+        n_blk = tile % num_n;
+        int m = tile / num_n;
+        w0 = (m % tiles_w) * CROW_PW;
+        m /= tiles_w;
+        h0 = (m % tiles_h) * 2;
+        t = m / tiles_h;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int t, h0, w0, n_blk;
+                tile_coords(tile, t, h0, w0, n_blk);
+                for (int dt = 0; dt < p.KT; ++dt)
+                    for (int dh = 0; dh < 3; ++dh)
+                        for (int kc = 0; kc < kc_per_tap; ++kc) {
+                            mbar_wait(empty_bar(stage), phase ^ 1, 61);
+                            const uint32_t sa = smem_base + stage * CROW_STAGE_BYTES;
+                            mbar_expect_tx(full_bar(stage), CROW_TX_BYTES);
+                            tma_load_4d(sa, &tmap_x, full_bar(stage), kc * CONV_BK, w0 - 1, h0 + dh - 1, t + dt - (p.KT - 1));
+                            const int tap0 = (dt * 3 + dh) * 3;
+#pragma unroll
+                            for (int dw = 0; dw < 3; ++dw)
+                                tma_load_2d(sa + CROW_A_BYTES + dw * CROW_B_BYTES, &tmap_w, full_bar(stage),
+                                            (tap0 + dw) * p.Cin + kc * CONV_BK, n_blk * BN);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one_sync();
+        constexpr uint32_t idesc = umma_idesc_bf16(CONV_BM, BN, 0, 0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1, 62);
+            tc_fence_after();
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(full_bar(stage), phase, 63);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * CROW_STAGE_BYTES;
+                if (leader) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {       // output row h0 + i reads input row slot i of the box
+                        const uint32_t d_tmem = tmem_base + acc * 256 + i * 128;
+#pragma unroll
+                        for (int dw = 0; dw < 3; ++dw) {
+                            const uint64_t da = umma_desc_kmajor_sw128(sa + (i * CROW_A_ROWS + dw) * 128);
+                            const uint64_t db = umma_desc_kmajor_sw128(sa + CROW_A_BYTES + dw * CROW_B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < CONV_BK / 16; ++k)
+                                umma_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | dw | k) != 0);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (leader) umma_commit(tfull_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const int sub = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int t, h0, w0, n_blk;
+            tile_coords(tile, t, h0, w0, n_blk);
+            mbar_wait(tfull_bar(acc), acc_phase, 64);
+            tc_fence_after();
+            const int w = w0 + sub * 32 + lane;
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+                const int h = h0 + i;
+                const bool pix_ok = h < p.H && w < p.W;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * 256 + i * 128;
+                const int64_t pix = (static_cast<int64_t>(t) * p.H + h) * p.W + w;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n_blk * BN + c * 32;
+                    if (col0 >= p.Cout) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c * 32, v);
+                    tmem_ld_wait();
+                    if (!pix_ok) continue;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = col0 + g * 8;
+                        if (col < p.Cout) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                            if (p.bias) {
+                                uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
+                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 b2 = unpack_bf16(bw[j]);
+                                    f[2 * j] += b2.x;
+                                    f[2 * j + 1] += b2.y;
+                                }
+                            }
+                            if (p.epilogue == CONV_EPI_BIAS_RES) {
+                                uint4 rv = *reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + col);
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 r2 = unpack_bf16(rw[j]);
+                                    f[2 * j] += r2.x;
+                                    f[2 * j + 1] += r2.y;
+                                }
+                            }
+                            uint4 ov;
+                            ov.x = pack_bf16(f[0], f[1]);
+                            ov.y = pack_bf16(f[2], f[3]);
+                            ov.z = pack_bf16(f[4], f[5]);
+                            ov.w = pack_bf16(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col) = ov;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------ VAE elementwise kernels (channels-last)
 
 // RMS_norm over channels (F.normalize(x, dim=C) * sqrt(C) * gamma, wan_vae.py:39-54) followed by SiLU.

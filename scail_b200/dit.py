@@ -289,6 +289,12 @@ class AdaLNMixin(BaseMixin):
         self.clip_feature_key_value_list = nn.ModuleList(
             [_Linear(hidden_size, 2 * hidden_size) for _ in range(num_layers)])
         self.cp = None  # scail_b200.parallel.ContextParallel or None
+        # text / CLIP K,V of every layer depend only on the prompt and the reference image,
+        # yet the reference recomputes them in all 40 blocks of all 50 steps (dit_video_crossattn_sc_xc.py:1117-1130).
+        # With cache_cross_kv=True they are computed once per (context, clip) tensor pair and reused — numerically
+        # identical.  bench.py keeps it OFF so that the timed step does the reference's full work.
+        self.cache_cross_kv = False
+        self._xkv_cache = {}
 
     # -- hooks ---------------------------------------------------------------------------------
     def layer_forward(self, hidden_states, mask, *args, **kwargs):
@@ -369,13 +375,21 @@ class AdaLNMixin(BaseMixin):
         xq = _WS.get("xq", (B * N, d), dev)
         ops.gemm(hidden_states.view(B * N, d), c.query.weight, c.query.bias, out=xq)
         ops.rmsnorm_rope(xq, N, d, [(0, self.cross_query_layernorm_list[l].weight)], eps=eps)
-        tkv = _WS.get("tkv", (B * Lt, 2 * d), dev)
-        ops.gemm(text.view(B * Lt, d), c.key_value.weight, c.key_value.bias, out=tkv)
-        ops.rmsnorm_rope(tkv, Lt, d, [(0, self.cross_key_layernorm_list[l].weight)], eps=eps)
-        ckv_lin = self.clip_feature_key_value_list[l]
-        ckv = _WS.get("ckv", (B * Lc, 2 * d), dev)
-        ops.gemm(clip.view(B * Lc, d), ckv_lin.weight, ckv_lin.bias, out=ckv)
-        ops.rmsnorm_rope(ckv, Lc, d, [(0, self.clip_feature_key_layernorm_list[l].weight)], eps=eps)
+        ckey = (l, text.data_ptr(), text._version, tuple(text.shape), clip.data_ptr(), clip._version, tuple(clip.shape))
+        cached = self._xkv_cache.get(l) if self.cache_cross_kv else None
+        if cached is not None and cached[0] == ckey:
+            tkv, ckv = cached[1], cached[2]
+        else:
+            keep = self.cache_cross_kv
+            tkv = torch.empty(B * Lt, 2 * d, device=dev, dtype=bf) if keep else _WS.get("tkv", (B * Lt, 2 * d), dev)
+            ops.gemm(text.view(B * Lt, d), c.key_value.weight, c.key_value.bias, out=tkv)
+            ops.rmsnorm_rope(tkv, Lt, d, [(0, self.cross_key_layernorm_list[l].weight)], eps=eps)
+            ckv_lin = self.clip_feature_key_value_list[l]
+            ckv = torch.empty(B * Lc, 2 * d, device=dev, dtype=bf) if keep else _WS.get("ckv", (B * Lc, 2 * d), dev)
+            ops.gemm(clip.view(B * Lc, d), ckv_lin.weight, ckv_lin.bias, out=ckv)
+            ops.rmsnorm_rope(ckv, Lc, d, [(0, self.clip_feature_key_layernorm_list[l].weight)], eps=eps)
+            if keep:
+                self._xkv_cache[l] = (ckey, tkv, ckv)
         ctx = _ctx_out if _ctx_out is not None else torch.empty(B * N, d, device=dev, dtype=bf)
         ops.attention(xq, tkv[:, :d], tkv[:, d:], ctx, B, H, N, Lt)
         ops.attention(xq, ckv[:, :d], ckv[:, d:], ctx, B, H, N, Lc, accumulate=True)
@@ -463,20 +477,27 @@ class DiffusionTransformer(nn.Module):
         bf = torch.bfloat16
         dev = context.device
         d = self.hidden_size
-        te = self.text_embedding
-        Lt = context.shape[1]
-        c2 = context.to(bf).contiguous().view(-1, self.text_dim)
-        t1 = ops.gemm(c2, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
-        text = ops.gemm(t1, te[2].weight, te[2].bias).view(context.shape[0], Lt, d)
-        p = self.clip_proj.proj
-        cf = clip_feats.to(device=dev, dtype=bf).contiguous()
-        Bc, Lc, dc = cf.shape
-        c0 = ops.ln_modulate(cf, gamma=p[0].weight, beta=p[0].bias, eps=p[0].eps)
-        c1 = ops.gemm(c0.view(Bc * Lc, dc), p[1].weight, p[1].bias, epilogue=ops.EPI_BIAS_GELU_ERF)
-        c3 = ops.gemm(c1, p[3].weight, p[3].bias).view(Bc, Lc, d)
-        clip = ops.ln_modulate(c3, gamma=p[4].weight, beta=p[4].bias, eps=p[4].eps)
-        if Bc != B:
-            clip = clip.repeat(B // Bc, 1, 1)  # :1512-1515
+        ad = self.mixins["adaln_layer"]
+        ekey = (context.data_ptr(), context._version, tuple(context.shape), clip_feats.data_ptr(), clip_feats._version, B)
+        if ad.cache_cross_kv and getattr(self, "_emb_cache", (None,))[0] == ekey:
+            text, clip = self._emb_cache[1], self._emb_cache[2]
+        else:
+            te = self.text_embedding
+            Lt = context.shape[1]
+            c2 = context.to(bf).contiguous().view(-1, self.text_dim)
+            t1 = ops.gemm(c2, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
+            text = ops.gemm(t1, te[2].weight, te[2].bias).view(context.shape[0], Lt, d)
+            p = self.clip_proj.proj
+            cf = clip_feats.to(device=dev, dtype=bf).contiguous()
+            Bc, Lc, dc = cf.shape
+            c0 = ops.ln_modulate(cf, gamma=p[0].weight, beta=p[0].bias, eps=p[0].eps)
+            c1 = ops.gemm(c0.view(Bc * Lc, dc), p[1].weight, p[1].bias, epilogue=ops.EPI_BIAS_GELU_ERF)
+            c3 = ops.gemm(c1, p[3].weight, p[3].bias).view(Bc, Lc, d)
+            clip = ops.ln_modulate(c3, gamma=p[4].weight, beta=p[4].bias, eps=p[4].eps)
+            if Bc != B:
+                clip = clip.repeat(B // Bc, 1, 1)  # :1512-1515
+            if ad.cache_cross_kv:
+                self._emb_cache = (ekey, text, clip)
         t_emb = ops.timestep_embedding(timesteps.to(device=dev, dtype=torch.float32).contiguous(), self.time_freq_dim)
         e1 = ops.gemm(t_emb, self.time_embed[0].weight, self.time_embed[0].bias, epilogue=ops.EPI_BIAS_SILU)
         emb = ops.gemm(e1, self.time_embed[2].weight, self.time_embed[2].bias)

@@ -26,7 +26,11 @@ def rnd(*s, seed=0, scale=1.0):
 
 @pytest.mark.parametrize("T,H,W,Cin,Cout,k", [(3, 8, 16, 64, 96, (3, 3, 3)), (2, 10, 20, 96, 192, (3, 3, 3)),
                                               (4, 16, 16, 16, 384, (3, 3, 3)), (3, 8, 8, 128, 256, (3, 1, 1)),
-                                              (2, 24, 40, 192, 96, (1, 3, 3)), (2, 16, 16, 384, 384, (3, 3, 3))])
+                                              (2, 24, 40, 192, 96, (1, 3, 3)), (2, 16, 16, 384, 384, (3, 3, 3)),
+                                              # W >= 128 and Cout % 96 == 0 -> row-tile kernel (taps = shifted smem views)
+                                              (2, 6, 128, 96, 96, (3, 3, 3)), (2, 5, 256, 192, 192, (3, 3, 3)),
+                                              (1, 4, 160, 64, 96, (3, 3, 3)), (2, 7, 384, 192, 96, (1, 3, 3)),
+                                              (3, 3, 128, 384, 384, (3, 3, 3))])
 def test_conv3d_cl_vs_torch(T, H, W, Cin, Cout, k):
     from scail_b200 import ops
     x = rnd(T, H, W, Cin, seed=1)
