@@ -108,6 +108,13 @@ enum { SCAIL_CONV_EPI_BIAS = 0, SCAIL_CONV_EPI_BIAS_RES = 1, SCAIL_CONV_EPI_HEAD
 int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin, const void* w2, int64_t Cout, int KT,
                     int KH, int KW, const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
                     int64_t ocols, int fmul, int epilogue, scail_stream_t stream);
+/* Strided variant for the encoder's Resample (wan_vae.py:87-96, 143-159): x [T_in,H_in,W_in,Cin] -> out [T_out,H_out,W_out,ldo];
+ * tap (dt,dh,dw) of output (t,h,w) reads input (t*tstride + dt + toff, h*sstride + dh - pad_h, w*sstride + dw - pad_w),
+ * out-of-range inputs are zero.  downsample2d/3d spatial conv: sstride 2, pads 0 (ZeroPad2d((0,1,0,1)));
+ * downsample3d time_conv: 3x1x1, tstride 2, toff 0 on frames 1.. (frame 0 bypasses it). */
+int scail_conv3d_strided_cl(const void* x, int64_t T_in, int64_t H_in, int64_t W_in, int64_t Cin, const void* w2, int64_t Cout,
+                            int KT, int KH, int KW, const void* bias, void* out, int64_t ldo, int64_t T_out, int64_t H_out,
+                            int64_t W_out, int sstride, int pad_h, int pad_w, int tstride, int toff, scail_stream_t stream);
 /* RMS_norm over channels (F.normalize * sqrt(C) * gamma, wan_vae.py:39-54), optional SiLU; [npix, C] bf16 */
 int scail_rmsnorm_cl(const void* x, const void* gamma, void* out, int64_t npix, int64_t C, int silu, scail_stream_t stream);
 /* nearest-exact 2x spatial upsample (wan_vae.py:57-63): [frames,H,W,C] -> [frames,2H,2W,C] */

@@ -89,3 +89,41 @@ def decode(sd, z, temperal_upsample=(True, True, False)):
     x = F.silu(rms_norm(x, sd["decoder.head.0.gamma"]))
     x = causal_conv3d(x, sd["decoder.head.2.weight"], sd["decoder.head.2.bias"])
     return x.float().clamp_(-1, 1)
+
+
+def downsample(sd, p, x, mode):
+    """Resample.forward (:101-160) for downsample2d / downsample3d, whole sequence.
+    Spatial: ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) per frame (:87-96).  Temporal (downsample3d): the first frame
+    bypasses time_conv (feat_cache None -> stored, :146-148); every later chunk convolves [last frame of the previous
+    chunk] + its own frames with a 3x1x1 kernel at stride 2 and no padding (:151-159), i.e. output k >= 1 is the window
+    of frames (2k-2, 2k-1, 2k) of the whole sequence."""
+    b, c, t, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    y = F.conv2d(F.pad(y, (0, 1, 0, 1)), sd[p + ".resample.1.weight"], sd[p + ".resample.1.bias"], stride=2)
+    y = y.reshape(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+    if mode == "downsample3d" and t > 1:
+        z = F.conv3d(y, sd[p + ".time_conv.weight"], sd[p + ".time_conv.bias"], stride=(2, 1, 1))
+        y = torch.cat([y[:, :, :1], z], 2)
+    return y
+
+
+def encode(sd, x, temperal_downsample=(False, True, True)):
+    """WanVAE_.encode (:516-542): x [b,3,T,H,W] (T = 1 + 4k) -> mu [b,16,1+k,H/8,W/8], scaled by (mu - mean) / std."""
+    sd = {k: v.float() for k, v in sd.items()}
+    x = causal_conv3d(x.float(), sd["encoder.conv1.weight"], sd["encoder.conv1.bias"])
+    idx = 0
+    for stage in range(4):
+        for _ in range(2):
+            x = residual_block(sd, f"encoder.downsamples.{idx}", x)
+            idx += 1
+        if stage < 3:
+            x = downsample(sd, f"encoder.downsamples.{idx}", x, "downsample3d" if temperal_downsample[stage] else "downsample2d")
+            idx += 1
+    x = residual_block(sd, "encoder.middle.0", x)
+    x = attention_block(sd, "encoder.middle.1", x)
+    x = residual_block(sd, "encoder.middle.2", x)
+    x = F.silu(rms_norm(x, sd["encoder.head.0.gamma"]))
+    x = causal_conv3d(x, sd["encoder.head.2.weight"], sd["encoder.head.2.bias"])
+    mu = causal_conv3d(x, sd["conv1.weight"], sd["conv1.bias"])[:, :16]
+    mean, std = torch.tensor(MEAN).view(1, 16, 1, 1, 1), torch.tensor(STD).view(1, 16, 1, 1, 1)
+    return (mu - mean) * (1.0 / std)

@@ -115,22 +115,23 @@ int make_tmap_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uin
 // 4-D bf16 channels-last activation [T, H, W, C]: dims (C, W, H, T), box (64, 16, 8, 1), SWIZZLE_128B.
 // Out-of-bounds box elements (channel tail, spatial halo, t < 0) are zero-filled.
 struct Map4Key {
-    const void* ptr; uint64_t T, H, W, C; uint32_t bw, bh;
-    bool operator==(const Map4Key& o) const { return ptr == o.ptr && T == o.T && H == o.H && W == o.W && C == o.C && bw == o.bw && bh == o.bh; }
+    const void* ptr; uint64_t T, H, W, C; uint32_t bw, bh, es;
+    bool operator==(const Map4Key& o) const { return ptr == o.ptr && T == o.T && H == o.H && W == o.W && C == o.C && bw == o.bw && bh == o.bh && es == o.es; }
 };
 struct Map4KeyHash {
     size_t operator()(const Map4Key& k) const {
         size_t h = reinterpret_cast<size_t>(k.ptr);
         auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.T); mix(k.H); mix(k.W); mix(k.C); mix(k.bw); mix(k.bh);
+        mix(k.T); mix(k.H); mix(k.W); mix(k.C); mix(k.bw); mix(k.bh); mix(k.es);
         return h;
     }
 };
 std::unordered_map<Map4Key, CUtensorMap, Map4KeyHash> g_maps4;
 
 int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t C, CUtensorMap* out, uint32_t box_w = 16,
-                   uint32_t box_h = 8) {
-    Map4Key key{ptr, T, H, W, C, box_w, box_h};
+                   uint32_t box_h = 8, uint32_t estride = 1) {
+    // estride = 2: the box spans box_w x box_h input pixels but only every second one is fetched (stride-2 conv)
+    Map4Key key{ptr, T, H, W, C, box_w, box_h, estride};
     {
         std::lock_guard<std::mutex> lk(g_map_mu);
         auto it = g_maps4.find(key);
@@ -142,7 +143,7 @@ int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t
     cuuint64_t gdim[4] = {C, W, H, T};
     cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
     cuuint32_t box[4] = {64, box_w, box_h, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t estr[4] = {1, estride, estride, 1};
     CUtensorMap m;
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -427,6 +428,7 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
     p.bias = static_cast<const __nv_bfloat16*>(bias); p.residual = static_cast<const __nv_bfloat16*>(residual);
     p.out = out; p.ldo = ldo; p.ldr = ldr; p.ocols = (int)(ocols > 0 ? ocols : Cout); p.fmul = fmul > 0 ? fmul : 1;
     p.epilogue = epilogue;
+    p.sstride = 1; p.pad_h = KH / 2; p.pad_w = KW / 2; p.tstride = 1; p.toff = -(KT - 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool row_ok_env = !(getenv("SCAIL_CONV_ROW") && atoi(getenv("SCAIL_CONV_ROW")) == 0);
     if (row_ok_env && KH == 3 && KW == 3 && W >= 128 && Cout % 96 == 0 && epilogue != CONV_EPI_HEAD_CLAMP && fmul <= 1 &&
@@ -443,6 +445,31 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
         SCAIL_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
+    if (BN == 16) return launch_conv<16>(tx, tw, p, st);
+    if (BN == 96) return launch_conv<96>(tx, tw, p, st);
+    return launch_conv<192>(tx, tw, p, st);
+}
+
+int scail_conv3d_strided_cl(const void* x, int64_t T_in, int64_t H_in, int64_t W_in, int64_t Cin, const void* w2, int64_t Cout,
+                            int KT, int KH, int KW, const void* bias, void* out, int64_t ldo, int64_t T_out, int64_t H_out,
+                            int64_t W_out, int sstride, int pad_h, int pad_w, int tstride, int toff, scail_stream_t stream) {
+    using namespace scail;
+    SCAIL_REQUIRE(x && w2 && out, "conv3d_strided: null operand");
+    SCAIL_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && ldo % 8 == 0, "conv3d_strided: channels must be multiples of 8");
+    SCAIL_REQUIRE((sstride == 1 || sstride == 2) && (tstride == 1 || tstride == 2), "conv3d_strided: strides must be 1 or 2");
+    SCAIL_REQUIRE(KT >= 1 && KT <= 3 && KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3, "conv3d_strided: taps must be 1..3");
+    const int taps = KT * KH * KW;
+    CUtensorMap tx, tw;
+    int rc;
+    if ((rc = make_tmap_cl4d(x, T_in, H_in, W_in, Cin, &tx, 16 * sstride, 8 * sstride, sstride))) return rc;
+    const int BN = Cout <= 16 ? 16 : (Cout <= 96 ? 96 : 192);
+    if ((rc = make_tmap_2d(w2, Cout, (uint64_t)taps * Cin, (uint64_t)taps * Cin, BN, 64, &tw))) return rc;
+    ConvParams p;
+    p.T = (int)T_out; p.H = (int)H_out; p.W = (int)W_out; p.Cin = (int)Cin; p.Cout = (int)Cout; p.KT = KT; p.KH = KH; p.KW = KW;
+    p.bias = static_cast<const __nv_bfloat16*>(bias); p.residual = nullptr; p.out = out; p.ldo = ldo; p.ldr = 0;
+    p.ocols = (int)Cout; p.fmul = 1; p.epilogue = CONV_EPI_BIAS;
+    p.sstride = sstride; p.pad_h = pad_h; p.pad_w = pad_w; p.tstride = tstride; p.toff = toff;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (BN == 16) return launch_conv<16>(tx, tw, p, st);
     if (BN == 96) return launch_conv<96>(tx, tw, p, st);
     return launch_conv<192>(tx, tw, p, st);

@@ -26,6 +26,8 @@ struct ConvParams {
     const __nv_bfloat16* residual;  // channels-last [T, H, W, ldr]
     void* out;                      // bf16 channels-last [*, H, W, ldo]  or  fp32 [3, T, H, W] (head)
     int64_t ldo, ldr;
+    int sstride, pad_h, pad_w;  // input coordinate of tap (dh,dw) for output (h,w): (h*sstride + dh - pad_h, w*sstride + dw - pad_w)
+    int tstride, toff;          // input frame of tap dt for output frame t: t*tstride + dt + toff (causal stride 1: toff = -(KT-1))
     int ocols;            // output column c lands in frame t*fmul + c / ocols, channel c % ocols
     int fmul;             // (time_conv of upsample3d interleaves its two channel halves as two frames)
     int epilogue;
@@ -109,7 +111,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                 tile_coords(tile, t, h0, w0, n_blk);
                 for (int tap = 0; tap < taps; ++tap) {
                     const int dw = tap % p.KW, dh = (tap / p.KW) % p.KH, dt = tap / (p.KW * p.KH);
-                    const int ct = t + dt - (p.KT - 1), ch = h0 + dh - p.KH / 2, cw = w0 + dw - p.KW / 2;
+                    const int ct = t * p.tstride + dt + p.toff, ch = h0 * p.sstride + dh - p.pad_h, cw = w0 * p.sstride + dw - p.pad_w;
                     for (int kc = 0; kc < kc_per_tap; ++kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1, 51);
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -328,7 +330,7 @@ conv3d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                             mbar_wait(empty_bar(stage), phase ^ 1, 61);
                             const uint32_t sa = smem_base + stage * CROW_STAGE_BYTES;
                             mbar_expect_tx(full_bar(stage), CROW_TX_BYTES);
-                            tma_load_4d(sa, &tmap_x, full_bar(stage), kc * CONV_BK, w0 - 1, h0 + dh - 1, t + dt - (p.KT - 1));
+                            tma_load_4d(sa, &tmap_x, full_bar(stage), kc * CONV_BK, w0 - 1, h0 + dh - 1, t + dt + p.toff);
                             const int tap0 = (dt * 3 + dh) * 3;
 #pragma unroll
                             for (int dw = 0; dw < 3; ++dw)

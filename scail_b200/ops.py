@@ -200,6 +200,22 @@ def conv3d_cl(x, w2, bias, kt, kh, kw, cout, out=None, residual=None, fmul=1, oc
     return out
 
 
+def conv3d_strided_cl(x, w2, bias, kt, kh, kw, cout, out_shape, sstride=1, pad_h=0, pad_w=0, tstride=1, toff=0, out=None):
+    """Strided conv for the VAE encoder: x [T,H,W,Cin] -> out [T_out,H_out,W_out,cout] (see scail_conv3d_strided_cl)."""
+    _req(x), _req(w2)
+    T, H, W, Cin = x.shape
+    assert x.is_contiguous() and w2.is_contiguous() and w2.shape == (cout, kt * kh * kw * Cin)
+    To, Ho, Wo = out_shape
+    if out is None:
+        out = torch.empty(To, Ho, Wo, cout, device=x.device, dtype=torch.bfloat16)
+    assert out.is_contiguous() and out.shape[-1] == cout
+    _lib.check(_lib.lib().scail_conv3d_strided_cl(_ptr(x), T, H, W, Cin, _ptr(w2), cout, kt, kh, kw, _ptr(bias), _ptr(out), cout,
+                                                  To, Ho, Wo, sstride, pad_h, pad_w, tstride, toff, _stream()),
+               "scail_conv3d_strided_cl")
+    _count()
+    return out
+
+
 def rmsnorm_cl(x, gamma, silu=True, out=None):
     _req(x), _req(gamma)
     C = x.shape[-1]

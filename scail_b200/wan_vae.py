@@ -5,7 +5,7 @@ decode_first_stage expect (diffusion_video.py:225-236, :298-309).
 
 `WanVAE_` holds parameters under the reference's state_dict names (decoder.conv1.*, decoder.middle.N.*,
 decoder.upsamples.N.*, decoder.head.*, conv2.*), so `load_state_dict(torch.load("Wan2.1_VAE.pth"), strict=False)`
-fills it (encoder.* / conv1.* keys belong to the encode path, which is a "next" row of SURVEY §8f).
+fills it (decoder.* / conv2.* for decode, encoder.* / conv1.* for encode).
 
 Compute path (all kernels of libscail_b200.so, activations channels-last bf16 [T,H,W,C]):
   whole-sequence causal 3x3x3 convs as tcgen05 implicit GEMMs with fused bias / residual epilogues,
@@ -105,17 +105,40 @@ class AttentionBlock(nn.Module):  # wan_vae.py:223-262
         return out
 
 
-class Resample(nn.Module):  # wan_vae.py:66-160 (decoder modes only)
+class Resample(nn.Module):  # wan_vae.py:66-160
     def __init__(self, dim, mode):
         super().__init__()
-        assert mode in ("upsample2d", "upsample3d")
+        assert mode in ("upsample2d", "upsample3d", "downsample2d", "downsample3d")
         self.dim, self.mode = dim, mode
-        self.resample = nn.Sequential(nn.Upsample(scale_factor=(2.0, 2.0), mode="nearest-exact"),
-                                      _Conv2d(dim, dim // 2, 3, padding=1))
-        if mode == "upsample3d":
-            self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        if mode.startswith("upsample"):
+            self.resample = nn.Sequential(nn.Upsample(scale_factor=(2.0, 2.0), mode="nearest-exact"),
+                                          _Conv2d(dim, dim // 2, 3, padding=1))
+            if mode == "upsample3d":
+                self.time_conv = CausalConv3d(dim, dim * 2, (3, 1, 1), padding=(1, 0, 0))
+        else:
+            self.resample = nn.Sequential(nn.ZeroPad2d((0, 1, 0, 1)), _Conv2d(dim, dim, 3, stride=(2, 2)))
+            if mode == "downsample3d":
+                self.time_conv = CausalConv3d(dim, dim, (3, 1, 1), stride=(2, 1, 1), padding=(0, 0, 0))
+
+    def run_down(self, x):
+        """Encoder path (wan_vae.py:138-160): per-frame ZeroPad2d((0,1,0,1)) + 3x3 stride-2 conv, then for downsample3d
+        the stride-2 time_conv over frames (2k-2, 2k-1, 2k) for k >= 1 while frame 0 bypasses it (first chunk only
+        fills the cache, :146-148)."""
+        T, H, W, C = x.shape
+        c2 = self.resample[1]
+        y = ops.conv3d_strided_cl(x, c2.packed(), c2.bias, 1, 3, 3, C, (T, H // 2, W // 2), sstride=2)
+        if self.mode == "downsample3d" and T > 1:
+            To = 1 + (T - 1) // 2
+            z = torch.empty(To, H // 2, W // 2, C, device=x.device, dtype=torch.bfloat16)
+            z[0].copy_(y[0])
+            tc = self.time_conv
+            ops.conv3d_strided_cl(y, tc.packed(), tc.bias, 3, 1, 1, C, (To - 1, H // 2, W // 2), tstride=2, toff=0, out=z[1:])
+            y = z
+        return y
 
     def run(self, x):
+        if self.mode.startswith("downsample"):
+            return self.run_down(x)
         T, H, W, C = x.shape
         if self.mode == "upsample3d" and T > 1:
             # frame 0 bypasses time_conv ('Rep'); frames 1.. form a fresh causal sequence whose two output
@@ -128,6 +151,47 @@ class Resample(nn.Module):  # wan_vae.py:66-160 (decoder modes only)
         up = ops.upsample2x_cl(x)
         c2 = self.resample[1]
         return ops.conv3d_cl(up, c2.packed(), c2.bias, 1, 3, 3, C // 2)
+
+
+class Encoder3d(nn.Module):  # wan_vae.py:265-366
+    def __init__(self, dim=96, z_dim=32, dim_mult=(1, 2, 4, 4), num_res_blocks=2, attn_scales=(),
+                 temperal_downsample=(False, True, True), dropout=0.0):
+        super().__init__()
+        if list(attn_scales):
+            raise NotImplementedError("Wan2.1 VAE uses attn_scales=[]")
+        dims = [dim * u for u in [1] + list(dim_mult)]
+        self.conv1 = CausalConv3d(3, dims[0], 3, padding=1)
+        downs = []
+        for i, (in_dim, out_dim) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(num_res_blocks):
+                downs.append(ResidualBlock(in_dim, out_dim))
+                in_dim = out_dim
+            if i != len(dim_mult) - 1:
+                downs.append(Resample(out_dim, "downsample3d" if temperal_downsample[i] else "downsample2d"))
+        self.downsamples = nn.Sequential(*downs)
+        self.middle = nn.Sequential(ResidualBlock(out_dim, out_dim), AttentionBlock(out_dim), ResidualBlock(out_dim, out_dim))
+        self.head = nn.Sequential(RMS_norm(out_dim, images=False), nn.SiLU(), CausalConv3d(out_dim, z_dim, 3, padding=1))
+
+    def conv1_packed(self):
+        """[Cout, 27*8]: the 3 RGB input channels are zero-padded to 8 (TMA rows are 16-byte multiples)."""
+        w = self.conv1.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        if getattr(self, "_c1_key", None) != key:
+            wp = w.detach().permute(0, 2, 3, 4, 1)
+            wp = torch.cat([wp, torch.zeros(*wp.shape[:-1], 5, device=w.device, dtype=w.dtype)], -1)
+            self._c1 = wp.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+            self._c1_key = key
+        return self._c1
+
+    def run(self, x8):
+        x = ops.conv3d_cl(x8, self.conv1_packed(), self.conv1.bias, 3, 3, 3, self.conv1.weight.shape[0])
+        for m in self.downsamples:
+            x = m.run(x)
+        for m in self.middle:
+            x = m.run(x)
+        a = ops.rmsnorm_cl(x, self.head[0].gamma.view(-1), silu=True)
+        hc = self.head[2]
+        return ops.conv3d_cl(a, hc.packed(), hc.bias, 3, 3, 3, hc.weight.shape[0])
 
 
 class Decoder3d(nn.Module):  # wan_vae.py:369-472
@@ -170,6 +234,8 @@ class WanVAE_(nn.Module):
                  temperal_downsample=(False, True, True), dropout=0.0):
         super().__init__()
         self.z_dim = z_dim
+        self.encoder = Encoder3d(dim, z_dim * 2, dim_mult, num_res_blocks, attn_scales, tuple(temperal_downsample), dropout)
+        self.conv1 = CausalConv3d(z_dim * 2, z_dim * 2, 1)
         self.conv2 = CausalConv3d(z_dim, z_dim, 1)
         self.decoder = Decoder3d(dim, z_dim, dim_mult, num_res_blocks, attn_scales, tuple(temperal_downsample)[::-1], dropout)
 
@@ -188,7 +254,23 @@ class WanVAE_(nn.Module):
         return self.decoder.run(x).unsqueeze(0)
 
     def encode(self, x, scale):
-        raise NotImplementedError("Wan VAE encode is a 'next' row (SURVEY.md §8f rank 2); only decode is on the hot path")
+        """x [1,3,T,H,W] (T = 1 + 4k), values in [-1,1]; scale = [mean, 1/std].  Returns mu [1,16,1+k,H/8,W/8] fp32,
+        (mu - mean) / std (wan_vae.py:516-542).  Whole-sequence causal convolutions; see Resample.run_down for the
+        first-frame rule of the temporal downsampling."""
+        if not x.is_cuda:
+            raise RuntimeError("scail_b200 has no CPU path: the VAE encode needs a CUDA (sm_100a) device")
+        assert x.shape[0] == 1 and x.shape[1] == 3
+        _, _, T, H, W = x.shape
+        x8 = torch.zeros(T, H, W, 8, device=x.device, dtype=torch.bfloat16)
+        x8[..., :3] = x[0].permute(1, 2, 3, 0)
+        y = self.encoder.run(x8)  # [T', h, w, 32]
+        Tp, h, w, C = y.shape
+        c1 = self.conv1
+        y = ops.gemm(y.view(-1, C), c1.weight.view(C, C), c1.bias).view(Tp, h, w, C)
+        mu = y[..., :self.z_dim].float().permute(3, 0, 1, 2)[None]
+        mean = scale[0].to(device=x.device, dtype=torch.float32).view(1, -1, 1, 1, 1)
+        inv_std = scale[1].to(device=x.device, dtype=torch.float32).view(1, -1, 1, 1, 1)
+        return (mu - mean) * inv_std
 
 
 class WanVAE:
@@ -206,7 +288,8 @@ class WanVAE:
         self.model = self.model.eval().requires_grad_(False).to(device).to(torch.bfloat16)
 
     def encode(self, videos):
-        raise NotImplementedError("Wan VAE encode is a 'next' row (SURVEY.md §8f rank 2)")
+        """videos: list of [3, T, H, W] tensors (wan_vae.py:648-657)."""
+        return torch.cat([self.model.encode(u.unsqueeze(0), self.scale).float() for u in videos], dim=0)
 
     def decode(self, zs):
         return torch.cat([self.model.decode(u.unsqueeze(0), self.scale).float().clamp_(-1, 1) for u in zs], dim=0)

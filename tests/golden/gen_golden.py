@@ -140,6 +140,13 @@ def gen_vae():
         sd = {k: v.to(torch.bfloat16) for k, v in vae.state_dict().items()
               if k.startswith("decoder.") or k.startswith("conv2.")}
         res[tag] = {"dim": dim, "z": z, "out": out, "state_dict": sd}
+        # encode path: video [1,3,9,32,32] -> mu [1,16,3,4,4]
+        video = torch.randn(1, 3, 9, 32, 32, generator=g).clamp(-1, 1).to(torch.bfloat16).float()
+        mu = vae.encode(video, scale).float()
+        esd = {k: v.to(torch.bfloat16) for k, v in vae.state_dict().items()
+               if k.startswith("encoder.") or k.startswith("conv1.")}
+        torch.save({"dim": dim, "video": video, "mu": mu, "state_dict": esd}, os.path.join(OUT, "vae_encode_small.pt"))
+        print("vae encode", tag, tuple(mu.shape), float(mu.abs().mean()))
         print("vae", tag, tuple(out.shape), float(out.abs().mean()))
     torch.save(res["narrow"], os.path.join(OUT, "vae_small.pt"))
     return res

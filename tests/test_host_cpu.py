@@ -79,7 +79,10 @@ def test_state_dict_names_match_reference_golden():
     gv = torch.load(os.path.join(GOLD, "vae_small.pt"))
     v = WanVAE(dim=gv["dim"], device="cpu")
     ours = {k: tuple(t.shape) for k, t in v.model.state_dict().items()}
-    assert ours == {k: tuple(t.shape) for k, t in gv["state_dict"].items()}
+    ge = torch.load(os.path.join(GOLD, "vae_encode_small.pt"))
+    ref = {k: tuple(t.shape) for k, t in gv["state_dict"].items()}
+    ref.update({k: tuple(t.shape) for k, t in ge["state_dict"].items()})
+    assert ours == ref  # decoder.* + conv2.* (decode) and encoder.* + conv1.* (encode): the whole Wan2.1_VAE.pth layout
 
 
 def test_sampler_schedule_matches_golden():

@@ -67,3 +67,10 @@ def test_vae_decode_matches_reference():
     out = V.decode(g["state_dict"], g["z"])
     assert out.shape == g["out"].shape
     assert rel(out, g["out"]) < 1e-5
+
+
+def test_vae_encode_matches_reference():
+    g = torch.load(os.path.join(GOLD, "vae_encode_small.pt"))
+    mu = V.encode(g["state_dict"], g["video"])
+    assert mu.shape == g["mu"].shape
+    assert rel(mu, g["mu"]) < 1e-5
