@@ -61,7 +61,8 @@ def build(force=False, verbose=False):
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "api.cu"), "-lcudart"]
+    extra = os.environ.get("SCAIL_NVCC_EXTRA", "").split()  # e.g. -DSCAIL_ATTN_EXPERIMENTS for scripts/trace_attn.py
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", LIB_PATH, os.path.join(CSRC, "api.cu"), "-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

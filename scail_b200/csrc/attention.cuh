@@ -15,6 +15,18 @@
 #pragma once
 #include "sm100.cuh"
 
+// Perf-experiment hooks (ablation modes via SCAIL_ATTN_DEBUG, clock64 traces via scail_debug_set_attention_trace) are
+// compiled only with -DSCAIL_ATTN_EXPERIMENTS (see scripts/trace_attn.py); the product build carries none of them.
+#ifdef SCAIL_ATTN_EXPERIMENTS
+#define SCAIL_ATTN_IF_NOT_DEBUG2 if (p.debug != 2)
+#define SCAIL_ATTN_TRACE_DECL(...) __VA_ARGS__
+#define SCAIL_ATTN_TRACE(IDX) if (tr) p.trace[IDX] = clock64()
+#else
+#define SCAIL_ATTN_IF_NOT_DEBUG2
+#define SCAIL_ATTN_TRACE_DECL(...)
+#define SCAIL_ATTN_TRACE(IDX)
+#endif
+
 namespace scail {
 
 constexpr int ATT_D = 128;
@@ -211,7 +223,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint64_t v_desc0 = umma_desc_mnmajor_sw128(v_smem, ATT_HALF_BYTES);
             constexpr uint64_t STAGE_STEP = ATT_TILE_BYTES >> 4;  // descriptor address units are 16 B
             auto issue_qk = [&](int tile, int ks) {
+#ifdef SCAIL_ATTN_EXPERIMENTS
                 if (p.debug == 5) return;
+#endif
                 const uint32_t d = tmem_base + tile * 128;
                 const uint64_t qa = tile ? q_desc1 : q_desc0, kb = k_desc0 + ks * STAGE_STEP;
                 if (leader) {
@@ -223,7 +237,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
             };
             auto issue_pv = [&](int tile, int vs, bool acc) {
+#ifdef SCAIL_ATTN_EXPERIMENTS
                 if (p.debug == 6) return;
+#endif
                 const uint32_t d = tmem_base + 256 + tile * 128;
                 const uint32_t a = tmem_base + tile * 128;  // P aliases S columns [0,64)
                 const uint64_t vb = v_desc0 + vs * STAGE_STEP;
@@ -253,10 +269,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const int ks = (j + 1) % ATT_KV_STAGES;
                 const uint32_t kph = ((j + 1) / ATT_KV_STAGES) & 1;
                 mbar_wait(bar(B_VFULL + vs), vph, 22);
-                const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && leader;
-                if (tr) p.trace[j * 8 + 0] = clock64();
-                if (p.debug != 2) mbar_wait(bar(B_PFULL + 0), j & 1, 23);
-                if (tr) p.trace[j * 8 + 1] = clock64();
+                SCAIL_ATTN_TRACE_DECL(const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && leader;)
+                SCAIL_ATTN_TRACE(j * 8 + 0);
+                SCAIL_ATTN_IF_NOT_DEBUG2 mbar_wait(bar(B_PFULL + 0), j & 1, 23);
+                SCAIL_ATTN_TRACE(j * 8 + 1);
                 tc_fence_after();
                 issue_pv(0, vs, j > 0);
                 if (more) {
@@ -264,12 +280,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_after();
                     issue_qk(0, ks);
                     commit(B_SFULL + 0);
-                    if (tr) p.trace[j * 8 + 2] = clock64();
+                    SCAIL_ATTN_TRACE(j * 8 + 2);
                 } else {
                     commit(B_OFULL + 0);
                 }
-                if (p.debug != 2) mbar_wait(bar(B_PFULL + 1), j & 1, 25);
-                if (tr) p.trace[j * 8 + 3] = clock64();
+                SCAIL_ATTN_IF_NOT_DEBUG2 mbar_wait(bar(B_PFULL + 1), j & 1, 25);
+                SCAIL_ATTN_TRACE(j * 8 + 3);
                 tc_fence_after();
                 issue_pv(1, vs, j > 0);
                 commit(B_VEMPTY + vs);
@@ -293,12 +309,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         float m_run = -INFINITY;  // running max, already multiplied by scale_log2
         float l_run = 0.f;
         for (int j = 0; j < n_kv; ++j) {
-            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
-            if (tr) p.trace[j * 8 + 4] = clock64();
+            SCAIL_ATTN_TRACE_DECL(const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;)
+            SCAIL_ATTN_TRACE(j * 8 + 4);
             mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
-            if (tr) p.trace[j * 8 + 5] = clock64();
+            SCAIL_ATTN_TRACE(j * 8 + 5);
             tc_fence_after();
             const int valid = p.kv_len - j * ATT_BKV;  // >= 128 except on the last tile
+#ifdef SCAIL_ATTN_EXPERIMENTS
             if (p.debug == 3) {  // TMEM read only
                 uint32_t t0[32], t1[32], t2[32], t3[32];
                 tmem_ld_32x32(s_tmem + 0, t0);
@@ -318,6 +335,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 l_run = 1.f;
                 continue;
             }
+#endif
             if (valid < ATT_BKV)  // warp-uniform; a separate instantiation keeps the 128 compare/selects off the hot path
                 softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
             else

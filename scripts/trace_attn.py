@@ -1,3 +1,6 @@
+"""Per-iteration clock64 trace of attention CTA (0,0,0).  Needs the experiment hooks compiled in:
+    SCAIL_NVCC_EXTRA=-DSCAIL_ATTN_EXPERIMENTS python -c "from scail_b200 import _lib; _lib.build(force=True)"
+(ablation modes: SCAIL_ATTN_DEBUG=1 softmax skipped, 2 MMA ignores P barriers, 3 TMEM read only, 5 PV only, 6 QK only)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scail_b200 import ops, _lib
