@@ -261,7 +261,8 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     p.ldc = ldc; p.ldr = ldr; p.gate_stride = gate_stride;
     p.rows_per_batch = rows_per_batch > 0 ? (int)rows_per_batch : (int)M;
     p.epilogue = epilogue;
-    p.group_m = 24;
+    static const int gm_env = getenv("SCAIL_GEMM_GROUP_M") ? atoi(getenv("SCAIL_GEMM_GROUP_M")) : 0;
+    p.group_m = gm_env > 0 ? gm_env : 24;
     if ((rc = set_smem(gemm_bf16_kernel, GEMM_SMEM_BYTES))) return rc;
     const int num_tiles = blocks_for(M, GEMM_BM) * blocks_for(N, GEMM_BN);
     const int sms = sm_count();

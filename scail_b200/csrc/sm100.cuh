@@ -74,9 +74,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
             uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > SCAIL_MBAR_TIMEOUT_NS) {
+#ifdef SCAIL_MBAR_DEBUG  // the printf costs registers / a stack frame in every kernel that waits; off in product builds
                 printf("scail: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
                        blockIdx.y, blockIdx.z, threadIdx.x, parity);
-                __trap();
+#endif
+                __trap();  // a protocol bug surfaces as a launch error instead of a hung GPU
             }
         }
     }
