@@ -432,17 +432,24 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
     p.sstride = 1; p.pad_h = KH / 2; p.pad_w = KW / 2; p.tstride = 1; p.toff = -(KT - 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool row_ok_env = !(getenv("SCAIL_CONV_ROW") && atoi(getenv("SCAIL_CONV_ROW")) == 0);
-    if (row_ok_env && KH == 3 && KW == 3 && W >= 128 && Cout % 96 == 0 && epilogue != CONV_EPI_HEAD_CLAMP && fmul <= 1 &&
-        (ocols <= 0 || ocols == Cout)) {
-        // row-tile kernel: 2 output rows x 128 pixels x 96 channels per iteration, taps as shifted smem views
+    const bool row_head = epilogue == CONV_EPI_HEAD_CLAMP && Cout <= 16;
+    if (row_ok_env && KH == 3 && KW == 3 && W >= 128 && (Cout % 96 == 0 || row_head) && fmul <= 1 && (ocols <= 0 || ocols == Cout)) {
+        // row-tile kernel: 2 output rows x 128 pixels x BN channels per iteration, taps as shifted smem views
+        const int RBN = row_head ? 16 : 96;
         CUtensorMap txr, twr;
         if ((rc = make_tmap_cl4d(x, T, H, W, Cin, &txr, CROW_A_ROWS, 2))) return rc;
-        if ((rc = make_tmap_2d(w2, Cout, (uint64_t)taps * Cin, (uint64_t)taps * Cin, CROW_BN, 64, &twr))) return rc;
-        if ((rc = set_smem(conv3d_row_kernel, CROW_SMEM_BYTES))) return rc;
-        const int tiles = (int)(T * ((H + 1) / 2) * blocks_for(W, CROW_PW) * blocks_for(Cout, CROW_BN));
+        if ((rc = make_tmap_2d(w2, Cout, (uint64_t)taps * Cin, (uint64_t)taps * Cin, RBN, 64, &twr))) return rc;
+        const int tiles = (int)(T * ((H + 1) / 2) * blocks_for(W, CROW_PW) * blocks_for(Cout, RBN));
         const int sms = sm_count();
         SCAIL_REQUIRE(sms > 0, "conv3d: no CUDA device");
-        conv3d_row_kernel<<<tiles < sms ? tiles : sms, CONV_THREADS, CROW_SMEM_BYTES, st>>>(txr, twr, p);
+        const int grid = tiles < sms ? tiles : sms;
+        if (row_head) {
+            if ((rc = set_smem(conv3d_row_kernel<16>, ConvRowCfg<16>::SMEM_BYTES))) return rc;
+            conv3d_row_kernel<16><<<grid, CONV_THREADS, ConvRowCfg<16>::SMEM_BYTES, st>>>(txr, twr, p);
+        } else {
+            if ((rc = set_smem(conv3d_row_kernel<96>, ConvRowCfg<96>::SMEM_BYTES))) return rc;
+            conv3d_row_kernel<96><<<grid, CONV_THREADS, ConvRowCfg<96>::SMEM_BYTES, st>>>(txr, twr, p);
+        }
         SCAIL_CHECK_CUDA(cudaGetLastError());
         return 0;
     }

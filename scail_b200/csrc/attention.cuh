@@ -308,13 +308,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t o_tmem = tmem_base + lane_off + 256 + tile * 128;
         float m_run = -INFINITY;  // running max, already multiplied by scale_log2
         float l_run = 0.f;
-        for (int j = 0; j < n_kv; ++j) {
+        const int n_full = p.kv_len / ATT_BKV;  // full tiles; an optional partial tile follows (peeled: no per-iteration branch)
+        for (int j = 0; j < n_full; ++j) {
             SCAIL_ATTN_TRACE_DECL(const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;)
             SCAIL_ATTN_TRACE(j * 8 + 4);
             mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
             SCAIL_ATTN_TRACE(j * 8 + 5);
             tc_fence_after();
-            const int valid = p.kv_len - j * ATT_BKV;  // >= 128 except on the last tile
+            constexpr int valid = ATT_BKV;
 #ifdef SCAIL_ATTN_EXPERIMENTS
             if (p.debug == 3) {  // TMEM read only
                 uint32_t t0[32], t1[32], t2[32], t3[32];
@@ -336,10 +337,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 continue;
             }
 #endif
-            if (valid < ATT_BKV)  // warp-uniform; a separate instantiation keeps the 128 compare/selects off the hot path
-                softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
-            else
-                softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
+            softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, valid, j, m_run, l_run, bar(B_PFULL + tile));
+        }
+        if (n_full < n_kv) {  // partial last KV tile: masked instantiation
+            mbar_wait(bar(B_SFULL + tile), n_full & 1, 32 + tile);
+            tc_fence_after();
+            softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, p.kv_len - n_full * ATT_BKV, n_full, m_run, l_run, bar(B_PFULL + tile));
         }
         // ---- epilogue: O / l -> bf16 -> global ----
         mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);

@@ -255,17 +255,25 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 // simply advanced by whole 128-byte rows (measured on B200: the 128B swizzle is a function of the absolute shared
 // memory address, exactly as TMA wrote it, so no descriptor base_offset is needed), and the three weight slices
 // of the stage are shared by both rows: 70 KB feed 24 UMMAs (1152 cycles) = 62 B/clk/SM.
-constexpr int CROW_PW = 128, CROW_BN = 96, CROW_STAGES = 3;
+constexpr int CROW_PW = 128;
 constexpr int CROW_A_ROWS = CROW_PW + 2;                                       // 130 pixels per input row
 constexpr int CROW_A_BYTES = ((2 * CROW_A_ROWS * 128 + 1023) / 1024) * 1024;   // 33280 -> 33792
-constexpr int CROW_B_BYTES = CROW_BN * CONV_BK * 2;                            // 12288 per dw tap
-constexpr int CROW_STAGE_BYTES = CROW_A_BYTES + 3 * CROW_B_BYTES;              // 70656
-constexpr int CROW_SMEM_BYTES = CROW_STAGES * CROW_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t CROW_TX_BYTES = 2 * CROW_A_ROWS * 128 + 3 * CROW_B_BYTES;   // bytes the TMA engine reports per stage
+template <int BN>
+struct ConvRowCfg {  // BN = 96 (residual / resample convs) or 16 (head conv 96 -> 3, L2-bound: the MMAs are almost free)
+    static constexpr int B_BYTES = BN * CONV_BK * 2;                               // per dw tap
+    static constexpr int STAGE_BYTES = CROW_A_BYTES + ((3 * B_BYTES + 1023) / 1024) * 1024;
+    static constexpr int STAGES = BN > 16 ? 3 : 5;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr uint32_t TX_BYTES = 2 * CROW_A_ROWS * 128 + 3 * B_BYTES;      // bytes the TMA engine reports per stage
+};
 
+template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
-    constexpr int BN = CROW_BN, STAGES = CROW_STAGES;
+    using Cfg = ConvRowCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int CROW_STAGE_BYTES = Cfg::STAGE_BYTES, CROW_B_BYTES = Cfg::B_BYTES;
+    constexpr uint32_t CROW_TX_BYTES = Cfg::TX_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * CROW_STAGE_BYTES;
@@ -389,13 +397,32 @@ conv3d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * 256 + i * 128;
                 const int64_t pix = (static_cast<int64_t>(t) * p.H + h) * p.W + w;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < (BN + 31) / 32; ++c) {
                     const int col0 = n_blk * BN + c * 32;
                     if (col0 >= p.Cout) break;
                     uint32_t v[32];
-                    tmem_ld_32x32(t_row + c * 32, v);
+                    if constexpr (BN % 32 == 0) {
+                        tmem_ld_32x32(t_row + c * 32, v);
+                    } else {  // BN = 16
+                        uint32_t v16[16];
+                        tmem_ld_32x16(t_row + c * 32, v16);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[j + 16] = 0; }
+                    }
                     tmem_ld_wait();
                     if (!pix_ok) continue;
+                    if (p.epilogue == CONV_EPI_HEAD_CLAMP) {  // fp32 planes [Cout, T, H, W], clamp(-1, 1)
+                        float* o = static_cast<float*>(p.out);
+                        const int64_t plane = static_cast<int64_t>(p.T) * p.H * p.W;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            if (col0 + j < p.Cout) {
+                                const float f = __uint_as_float(v[j]) + __bfloat162float(p.bias[col0 + j]);
+                                o[(col0 + j) * plane + pix] = fminf(fmaxf(f, -1.0f), 1.0f);
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int col = col0 + g * 8;

@@ -68,6 +68,13 @@ def test_time_conv_interleave_and_head():
     want = F.conv3d(xin, wh.float(), bh.float())[0].clamp(-1, 1)
     assert got.dtype == torch.float32 and got.shape == want.shape
     assert float((got - want).abs().max()) < 2e-2
+    # same head conv at W >= 128: row-tile kernel instantiated with N = 16
+    x2 = rnd(2, 5, 256, 96, seed=7)
+    wh2, bh2 = rnd(3, 96, 3, 3, 3, seed=8, scale=0.04), rnd(3, seed=9)
+    got2 = ops.conv3d_cl(x2, wh2.permute(0, 2, 3, 4, 1).reshape(3, -1).contiguous(), bh2, 3, 3, 3, 3, head=True)
+    xin2 = F.pad(x2.float().permute(3, 0, 1, 2)[None], (1, 1, 1, 1, 2, 0))
+    want2 = F.conv3d(xin2, wh2.float(), bh2.float())[0].clamp(-1, 1)
+    assert got2.shape == want2.shape and float((got2 - want2).abs().max()) < 2e-2
 
 
 def test_vae_elementwise():
