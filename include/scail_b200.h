@@ -104,10 +104,13 @@ enum { SCAIL_CONV_EPI_BIAS = 0, SCAIL_CONV_EPI_BIAS_RES = 1, SCAIL_CONV_EPI_HEAD
  * padding (KT-1 zero frames on the left).  Output column c is written to frame t*fmul + c/ocols, channel
  * c%ocols of out [*, H, W, ldo] (fmul=2, ocols=Cout/2 interleaves time_conv's channel halves as frames,
  * wan_vae.py:134-137).  epilogue: +bias | +bias+residual [T,H,W,ldr] (ResidualBlock, :220) |
- * head: +bias, clamp(-1,1), fp32 planes [Cout, T, H, W] (:421, :662-664). */
+ * head: +bias, clamp(-1,1), fp32 planes [Cout, T, H, W] (:421, :662-664).
+ * norm_gamma/out2 (optional, Cout == 96, 3x3 taps, W >= 128): additionally write out2 [T,H,W,96] =
+ * SiLU(RMS_norm(value) * gamma), the input of the NEXT conv (ResidualBlock.residual[0..1] / [3..4], :194-198);
+ * out may then be NULL when the raw value is not needed. */
 int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin, const void* w2, int64_t Cout, int KT,
                     int KH, int KW, const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
-                    int64_t ocols, int fmul, int epilogue, scail_stream_t stream);
+                    int64_t ocols, int fmul, int epilogue, const void* norm_gamma, void* out2, scail_stream_t stream);
 /* Strided variant for the encoder's Resample (wan_vae.py:87-96, 143-159): x [T_in,H_in,W_in,Cin] -> out [T_out,H_out,W_out,ldo];
  * tap (dt,dh,dw) of output (t,h,w) reads input (t*tstride + dt + toff, h*sstride + dh - pad_h, w*sstride + dw - pad_w),
  * out-of-range inputs are zero.  downsample2d/3d spatial conv: sstride 2, pads 0 (ZeroPad2d((0,1,0,1)));

@@ -35,7 +35,7 @@ SIGNATURES = {
     "scail_cfg_euler": [c_p, c_p, c_i64, c_f, c_f, c_p],
     "scail_cast_f32_bf16": [c_p, c_p, c_i64, c_p],
     "scail_conv3d_cl": [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_int, c_int, c_int, c_p, c_p, c_i64, c_p, c_i64,
-                        c_i64, c_int, c_int, c_p],
+                        c_i64, c_int, c_int, c_p, c_p, c_p],
     "scail_conv3d_strided_cl": [c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_i64, c_int, c_int, c_int, c_p, c_p, c_i64, c_i64,
                                 c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_p],
     "scail_rmsnorm_cl": [c_p, c_p, c_p, c_i64, c_i64, c_int, c_p],

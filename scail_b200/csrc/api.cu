@@ -409,9 +409,12 @@ int scail_cast_f32_bf16(const float* x, void* out, int64_t n, scail_stream_t str
 
 int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin, const void* w2, int64_t Cout, int KT,
                     int KH, int KW, const void* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
-                    int64_t ocols, int fmul, int epilogue, scail_stream_t stream) {
+                    int64_t ocols, int fmul, int epilogue, const void* norm_gamma, void* out2, scail_stream_t stream) {
     using namespace scail;
-    SCAIL_REQUIRE(x && w2 && out, "conv3d: null operand");
+    SCAIL_REQUIRE(x && w2 && (out || (norm_gamma && out2)), "conv3d: null operand");
+    SCAIL_REQUIRE((norm_gamma == nullptr) == (out2 == nullptr), "conv3d: norm_gamma and out2 come together");
+    if (norm_gamma) SCAIL_REQUIRE(KH == 3 && KW == 3 && W >= 128 && Cout == 96 && epilogue != CONV_EPI_HEAD_CLAMP && fmul <= 1,
+                                  "conv3d: the fused RMS_norm+SiLU output needs the row-tile kernel with Cout == 96 (3x3 taps, W >= 128)");
     SCAIL_REQUIRE(T > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout > 0, "conv3d: bad shape");
     SCAIL_REQUIRE(KT >= 1 && KT <= 3 && KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3 && (KH & 1) && (KW & 1), "conv3d: taps must be 1 or 3");
     SCAIL_REQUIRE(epilogue >= 0 && epilogue <= 2, "conv3d: unknown epilogue");
@@ -429,10 +432,12 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
     p.bias = static_cast<const __nv_bfloat16*>(bias); p.residual = static_cast<const __nv_bfloat16*>(residual);
     p.out = out; p.ldo = ldo; p.ldr = ldr; p.ocols = (int)(ocols > 0 ? ocols : Cout); p.fmul = fmul > 0 ? fmul : 1;
     p.epilogue = epilogue;
+    p.norm_gamma = static_cast<const __nv_bfloat16*>(norm_gamma); p.out2 = static_cast<__nv_bfloat16*>(out2);
     p.sstride = 1; p.pad_h = KH / 2; p.pad_w = KW / 2; p.tstride = 1; p.toff = -(KT - 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool row_ok_env = !(getenv("SCAIL_CONV_ROW") && atoi(getenv("SCAIL_CONV_ROW")) == 0);
     const bool row_head = epilogue == CONV_EPI_HEAD_CLAMP && Cout <= 16;
+    if (norm_gamma) SCAIL_REQUIRE(row_ok_env, "conv3d: fused norm output requested but SCAIL_CONV_ROW=0");
     if (row_ok_env && KH == 3 && KW == 3 && W >= 128 && (Cout % 96 == 0 || row_head) && fmul <= 1 && (ocols <= 0 || ocols == Cout)) {
         // row-tile kernel: 2 output rows x 128 pixels x BN channels per iteration, taps as shifted smem views
         const int RBN = row_head ? 16 : 96;
@@ -475,7 +480,7 @@ int scail_conv3d_strided_cl(const void* x, int64_t T_in, int64_t H_in, int64_t W
     ConvParams p;
     p.T = (int)T_out; p.H = (int)H_out; p.W = (int)W_out; p.Cin = (int)Cin; p.Cout = (int)Cout; p.KT = KT; p.KH = KH; p.KW = KW;
     p.bias = static_cast<const __nv_bfloat16*>(bias); p.residual = nullptr; p.out = out; p.ldo = ldo; p.ldr = 0;
-    p.ocols = (int)Cout; p.fmul = 1; p.epilogue = CONV_EPI_BIAS;
+    p.ocols = (int)Cout; p.fmul = 1; p.epilogue = CONV_EPI_BIAS; p.norm_gamma = nullptr; p.out2 = nullptr;
     p.sstride = sstride; p.pad_h = pad_h; p.pad_w = pad_w; p.tstride = tstride; p.toff = toff;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (BN == 16) return launch_conv<16>(tx, tw, p, st);

@@ -28,6 +28,8 @@ struct ConvParams {
     int64_t ldo, ldr;
     int sstride, pad_h, pad_w;  // input coordinate of tap (dh,dw) for output (h,w): (h*sstride + dh - pad_h, w*sstride + dw - pad_w)
     int tstride, toff;          // input frame of tap dt for output frame t: t*tstride + dt + toff (causal stride 1: toff = -(KT-1))
+    const __nv_bfloat16* norm_gamma;  // row-tile kernel, Cout == 96 only: also emit out2 = SiLU(RMS_norm(value) * gamma)
+    __nv_bfloat16* out2;              //   (the next conv's input, wan_vae.py:194-198) ; `out` may then be null
     int ocols;            // output column c lands in frame t*fmul + c / ocols, channel c % ocols
     int fmul;             // (time_conv of upsample3d interleaves its two channel halves as two frames)
     int epilogue;
@@ -396,6 +398,82 @@ conv3d_row_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const bool pix_ok = h < p.H && w < p.W;
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * 256 + i * 128;
                 const int64_t pix = (static_cast<int64_t>(t) * p.H + h) * p.W + w;
+                if constexpr (BN == 96) {
+                    if (p.norm_gamma != nullptr) {
+                        // Fused RMS_norm + SiLU of the NEXT conv's input: this thread holds all 96 channels of its pixel.
+                        uint32_t v[3][32];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) tmem_ld_32x32(t_row + c * 32, v[c]);
+                        tmem_ld_wait();
+                        if (!pix_ok) continue;
+                        float ss = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int col = c * 32 + g * 8;
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c][g * 8 + j]);
+                                if (p.bias) {
+                                    uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
+                                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 b2 = unpack_bf16(bw[j]);
+                                        f[2 * j] += b2.x;
+                                        f[2 * j + 1] += b2.y;
+                                    }
+                                }
+                                if (p.epilogue == CONV_EPI_BIAS_RES) {
+                                    uint4 rv = *reinterpret_cast<const uint4*>(p.residual + pix * p.ldr + col);
+                                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 r2 = unpack_bf16(rw[j]);
+                                        f[2 * j] += r2.x;
+                                        f[2 * j + 1] += r2.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    ss += f[j] * f[j];
+                                    v[c][g * 8 + j] = __float_as_uint(f[j]);
+                                }
+                                if (p.out) {
+                                    uint4 ov;
+                                    ov.x = pack_bf16(f[0], f[1]);
+                                    ov.y = pack_bf16(f[2], f[3]);
+                                    ov.z = pack_bf16(f[4], f[5]);
+                                    ov.w = pack_bf16(f[6], f[7]);
+                                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + col) = ov;
+                                }
+                            }
+                        }
+                        const float inv = 9.797958971132712f / fmaxf(sqrtf(ss), 1e-12f);  // sqrt(96) / max(||x||, eps)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int col = c * 32 + g * 8;
+                                uint4 gv = *reinterpret_cast<const uint4*>(p.norm_gamma + col);
+                                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                                uint32_t r[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 g2 = unpack_bf16(gw[j]);
+                                    float a = __uint_as_float(v[c][g * 8 + 2 * j]) * inv * g2.x;
+                                    float b = __uint_as_float(v[c][g * 8 + 2 * j + 1]) * inv * g2.y;
+                                    a = a / (1.0f + __expf(-a));
+                                    b = b / (1.0f + __expf(-b));
+                                    r[j] = pack_bf16(a, b);
+                                }
+                                *reinterpret_cast<uint4*>(p.out2 + pix * 96 + col) = make_uint4(r[0], r[1], r[2], r[3]);
+                            }
+                        }
+                        continue;
+                    }
+                }
 #pragma unroll 1
                 for (int c = 0; c < (BN + 31) / 32; ++c) {
                     const int col0 = n_blk * BN + c * 32;

@@ -177,27 +177,38 @@ def cast_bf16(x):
 CONV_EPI_BIAS, CONV_EPI_BIAS_RES, CONV_EPI_HEAD_CLAMP = range(3)
 
 
-def conv3d_cl(x, w2, bias, kt, kh, kw, cout, out=None, residual=None, fmul=1, ocols=None, head=False):
+def conv3d_fusable(x, kh, kw, cout):
+    """True when conv3d_cl can also emit SiLU(RMS_norm(out) * gamma) from its epilogue (row-tile kernel, Cout == 96)."""
+    return kh == 3 and kw == 3 and x.shape[2] >= 128 and cout == 96
+
+
+def conv3d_cl(x, w2, bias, kt, kh, kw, cout, out=None, residual=None, fmul=1, ocols=None, head=False, norm_gamma=None,
+              want_raw=True):
     """x [T,H,W,Cin] bf16 channels-last; w2 [cout, kt*kh*kw*Cin] bf16.  Returns out [T*fmul,H,W,ocols] bf16
-    (or fp32 planes [cout,T,H,W] when head=True)."""
+    (or fp32 planes [cout,T,H,W] when head=True).  With norm_gamma (see conv3d_fusable) returns (out, out2) where
+    out2 = SiLU(RMS_norm(out) * gamma) comes from the same epilogue; want_raw=False skips writing `out` (returned None)."""
     _req(x), _req(w2)
     T, H, W, Cin = x.shape
     assert x.is_contiguous() and w2.is_contiguous() and w2.shape == (cout, kt * kh * kw * Cin)
     ocols = cout if ocols is None else ocols
+    out2 = None
     if head:
         if out is None:
             out = torch.empty(cout, T, H, W, device=x.device, dtype=torch.float32)
         epi, ldo = CONV_EPI_HEAD_CLAMP, 0
     else:
-        if out is None:
+        if norm_gamma is not None:
+            assert conv3d_fusable(x, kh, kw, cout) and fmul == 1
+            out2 = torch.empty(T, H, W, cout, device=x.device, dtype=torch.bfloat16)
+        if out is None and (want_raw or norm_gamma is None):
             out = torch.empty(T * fmul, H, W, ocols, device=x.device, dtype=torch.bfloat16)
-        epi, ldo = (CONV_EPI_BIAS_RES if residual is not None else CONV_EPI_BIAS), out.shape[-1]
-        assert out.is_contiguous()
+        epi, ldo = (CONV_EPI_BIAS_RES if residual is not None else CONV_EPI_BIAS), (out.shape[-1] if out is not None else cout)
+        assert out is None or out.is_contiguous()
     _lib.check(_lib.lib().scail_conv3d_cl(_ptr(x), T, H, W, Cin, _ptr(w2), cout, kt, kh, kw, _ptr(bias), _ptr(residual),
                                           residual.shape[-1] if residual is not None else 0, _ptr(out), ldo, ocols, fmul,
-                                          epi, _stream()), "scail_conv3d_cl")
+                                          epi, _ptr(norm_gamma), _ptr(out2), _stream()), "scail_conv3d_cl")
     _count()
-    return out
+    return (out, out2) if norm_gamma is not None else out
 
 
 def conv3d_strided_cl(x, w2, bias, kt, kh, kw, cout, out_shape, sstride=1, pad_h=0, pad_w=0, tstride=1, toff=0, out=None):
