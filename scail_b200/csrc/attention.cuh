@@ -4,9 +4,12 @@
 // cross-attention calls (:1159-1197).
 //
 // One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong on the
-// tensor core.  Roles (10 warps):
+// tensor core.  Roles (12 warps = 3 warpgroups, registers re-split with setmaxnreg: 208 / 208 / 88):
 //   warps 0-3  softmax warpgroup for Q tile 0      warps 4-7  softmax warpgroup for Q tile 1
-//   warp  8    TMA producer (Q once, K/V rings)     warp  9    tcgen05.mma issuer + TMEM owner
+//   warp  8    TMA producer (Q once, K/V rings)     warp  9    tcgen05.mma issuer + TMEM owner   (10, 11 idle)
+// The MMA warp keeps its control flow warp-uniform (all lanes wait on the mbarriers; descriptors are computed in
+// uniform registers) and only the tcgen05 instructions are issued by the elected lane: with the issue loop inside a
+// divergent `if (lane == 0)` each tcgen05.mma cost ~80 cycles to issue, more than a 64-cycle 128x128x16 MMA runs.
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16) aliases the first 64
 // columns of its S buffer and feeds the PV product as the TMEM A operand (no smem round trip).
 // S = Q K^T : UMMA 128x128x16, A/B K-major from smem (TMA SWIZZLE_128B).

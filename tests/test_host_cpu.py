@@ -120,3 +120,20 @@ def test_mixins_plug_into_reference_model():
                  "attention_forward", "cross_attention_forward"):
         assert hook in mine.hooks, hook
     importlib.reload(ours)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm: oracle port on the host cores, bounded sample) prints one JSON line with
+    the contract's keys.  Uses a reduced sample so the CPU suite stays short."""
+    import json
+    import subprocess
+    code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0'];"
+            "import bench; bench.cpu_baseline.__defaults__=(3,16,16,None); bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and d["config"]["seq_len"] == 27904
