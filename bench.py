@@ -14,7 +14,13 @@ all-gather per block (scail_b200.parallel); strong scaling (the step is fixed, r
 
 --impl reference: the reference's own CPU implementation of the path cannot travel to the GPU box
 (/root/reference is absent there), so this arm times the oracle port (oracle/dit_oracle.py, fp32, all host
-threads) on a bounded sample — one full-width block on a reduced latent — and FLOP-scales it to steps/s.
+threads) on a bounded sample — ONE full-width block at the full N = 27 904, b=1 — and scales it
+by the 40 layers x 2 CFG branches it stands for (machine-readable: cpu_baseline.extrapolated / .extrapolation_factor).
+
+--impl torchlib: the SAME step (same weights, same inputs, same N) on the PyTorch library path the reference
+actually runs on a GPU (cuBLASLt F.linear, flash/cuDNN SDPA, F.layer_norm; baseline/torchlib.py).  The default arm
+also times it after its own timed region and reports `library_baseline`, plus per-kernel `kernel_compare`
+(ours vs cuBLAS / SDPA at the step's shapes) and `vae_decode` (config 5, ours vs cuDNN conv3d) at N=1.
 """
 import argparse
 import json
@@ -36,7 +42,9 @@ N_TEXT, N_CLIP = 512, 257
 NCU_ATTN_DRAM_BYTES = 1.727272e9 + 0.562356e9  # per self-attention launch (b=2, 40 heads, N=27904), profiles/r01b_ncu_summary.md
 
 
-def seq_len(t=T_LAT, h=H_LAT, w=W_LAT):
+def seq_len(t=None, h=None, w=None):
+    """ref + noise + pose tokens; defaults are read at CALL time so that --latent reaches every caller."""
+    t, h, w = (T_LAT if t is None else t), (H_LAT if h is None else h), (W_LAT if w is None else w)
     return h * w // 4 + t * h * w // 4 + t * (h // 2) * (w // 2) // 4
 
 
@@ -123,14 +131,7 @@ def build_model(device, layers=LAYERS, seed=1234):
     return m.eval()
 
 
-def cpu_baseline(sample_t=9, sample_h=32, sample_w=32, threads=None):
-    """Oracle port (fp32, torch CPU kernels, all host threads) on a bounded sample: ONE full-width block, b=2,
-    latent [t,h,w] = [9,32,32] -> N = 256+2304+576 = 3136 tokens, FLOP-scaled to a 40-block b=2 step at N=27904."""
-    from oracle import dit_oracle as O
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    n = seq_len(sample_t, sample_h, sample_w)
-    g = torch.Generator().manual_seed(0)
+def _oracle_block_inputs(n, g):
     sd = {}
     def lin(name, o, i):
         sd[name + ".weight"] = torch.randn(o, i, generator=g) * 0.02
@@ -144,24 +145,54 @@ def cpu_baseline(sample_t=9, sample_h=32, sample_w=32, threads=None):
     for nm in ("query", "key", "cross_query", "cross_key", "clip_feature_key"):
         sd[f"mixins.adaln_layer.{nm}_layernorm_list.0.weight"] = torch.ones(D)
     sd["mixins.adaln_layer.adaLN_modulations.0"] = torch.randn(1, 6, D, generator=g) / D ** 0.5
-    x = torch.randn(2, n, D, generator=g)
-    emb = torch.randn(2, 6 * D, generator=g) * 0.1
-    text, clip = torch.randn(2, N_TEXT, D, generator=g), torch.randn(2, N_CLIP, D, generator=g)
-    cos, sin = O.rope_tables(128, sample_t, sample_h // 2, sample_w // 2, 21, 150, 150)
+    return sd
+
+
+def cpu_baseline(threads=None, budget_s=45.0):
+    """Oracle port (fp32, torch CPU kernels incl. the library SDPA the reference calls, all host threads) on a bounded
+    sample.  Preferred sample: ONE full-width block at the FULL sequence length, b=1 — the extrapolation is
+    then only x (40 layers x 2 CFG branches).  A calibration block on a 9x32x32 latent predicts its cost first; if the
+    prediction exceeds `budget_s` on this host the reduced sample itself is reported, FLOP-scaled (and says so)."""
+    from oracle import dit_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    O.USE_LIBRARY_SDPA = True  # F.scaled_dot_product_attention (what sat/transformer_defaults.py:67-72 calls): no N x N matrix
+    g = torch.Generator().manual_seed(0)
+    sd = _oracle_block_inputs(0, g)
+    text, clip = torch.randn(1, N_TEXT, D, generator=g), torch.randn(1, N_CLIP, D, generator=g)
+    emb = torch.randn(1, 6 * D, generator=g) * 0.1
+
+    def run(t, h, w):
+        n = seq_len(t, h, w)
+        x = torch.randn(1, n, D, generator=g)
+        cos, sin = O.rope_tables(128, t, h // 2, w // 2, 21, 150, 150)
+        with torch.no_grad():
+            t0 = time.time()
+            O.block(sd, 0, x, emb, HEADS, cos, sin, text, clip)
+            return n, time.time() - t0
+
     with torch.no_grad():
-        O.block(sd, 0, x[:, :32], emb, HEADS, cos[:32], sin[:32], text, clip)  # warm-up
-        t0 = time.time()
-        O.block(sd, 0, x, emb, HEADS, cos, sin, text, clip)
-        dt = time.time() - t0
-    sample_flops = 2 * block_flops(n)
+        run(4, 16, 16)  # warm-up (thread pool, allocator)
+        n_s, dt_s = run(9, 32, 32)
     step_flops = 2 * forward_flops(seq_len())
-    est_step_s = dt * step_flops / sample_flops
-    return {"value": 1.0 / est_step_s, "unit": "steps/s", "cores": threads, "kind": "port",
-            "sample": f"oracle/dit_oracle.py fp32: 1 full-width block (d=5120, f=13824, 40 heads), b=2, latent "
-                      f"{sample_t}x{sample_h}x{sample_w} (N={n} tokens) took {dt:.2f} s on {threads} threads; "
-                      f"EXTRAPOLATED by FLOPs ({step_flops / sample_flops:.0f}x) to the 40-block b=2 step at N=27904 "
-                      f"(~{est_step_s / 60:.0f} min/step); fp32 14B weights (64.6 GB) do not fit host RAM",
-            "sample_seconds": dt}
+    pred_full = dt_s * block_flops(seq_len()) / block_flops(n_s)
+    if pred_full <= budget_s:
+        n, dt = run(T_LAT, H_LAT, W_LAT)
+        factor = step_flops / block_flops(n)
+        sample = (f"oracle/dit_oracle.py fp32: 1 full-width block (d=5120, f=13824, 40 heads), b=1, FULL latent "
+                  f"{T_LAT}x{H_LAT}x{W_LAT} (N={n} tokens) took {dt:.2f} s on {threads} threads; EXTRAPOLATED x{factor:.1f} "
+                  f"(40 layers x 2 CFG branches + embed/final) to one sampler step; fp32 14B weights (64.6 GB) do not fit host RAM")
+        kind_note = "full-N block"
+    else:
+        n, dt = n_s, dt_s
+        factor = step_flops / block_flops(n)
+        sample = (f"oracle/dit_oracle.py fp32: 1 full-width block, b=1, REDUCED latent 9x32x32 (N={n}) took {dt:.2f} s on {threads} "
+                  f"threads (the full-N block was predicted at {pred_full:.0f} s > {budget_s:.0f} s budget); EXTRAPOLATED by FLOPs x{factor:.0f}")
+        kind_note = "reduced-N block"
+    est_step_s = dt * factor
+    return {"value": 1.0 / est_step_s, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample,
+            "sample_kind": kind_note, "sample_seconds": dt, "sample_tokens": n, "extrapolated": True,
+            "extrapolation_factor": factor, "est_step_seconds": est_step_s}
 
 
 def run_reference_arm(args):
@@ -170,7 +201,8 @@ def run_reference_arm(args):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline()
+        # warm-up iterations use a tiny budget (reduced sample) so that the whole arm stays within a few minutes
+        cb = cpu_baseline(budget_s=45.0 if i >= args.warmup else 0.0)
         if i >= args.warmup:
             vals.append(cb)
     v = statistics.mean(c["value"] for c in vals)
@@ -181,6 +213,100 @@ def run_reference_arm(args):
                       "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
                       "cpu_baseline": cb, "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0,
                                                   "d2h_bytes_per_step": 0}}))
+
+
+def _time_cuda(fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def kernel_compare(dev):
+    """Ours vs the library kernel the reference would launch, at the step's shapes (b=2 rows = 2 x N), isolated, CUDA events."""
+    from scail_b200 import ops
+    n = seq_len()
+    M = 2 * n
+    res = {}
+    for name, (N, K, epi) in {"qkv": (3 * D, D, 0), "attn_out": (D, D, 2), "fc1": (F, D, 1), "fc2": (D, F, 2)}.items():
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.01
+        b = torch.randn(N, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        kw = dict(gate=torch.randn(2, N, device=dev, dtype=torch.bfloat16), residual=out, rows_per_batch=n) if epi == 2 else {}
+        ms = _time_cuda(lambda: ops.gemm(a, w, b, out=out, epilogue=epi, **kw), 5, 2)
+        ms_t = _time_cuda(lambda: torch.nn.functional.linear(a, w, b), 5, 2)
+        res["gemm_" + name] = {"ours_ms": round(ms, 3), "cublas_ms": round(ms_t, 3), "ours_tflops": round(2 * M * N * K / ms / 1e9, 1),
+                               "ours_over_cublas": round(ms_t / ms, 3),
+                               "note": "ours includes the fused bias" + ("+GELU" if epi == 1 else "+gate+residual" if epi == 2 else "")
+                                       + " epilogue; cuBLAS = F.linear (bias only)"}
+        del a, w, out
+    qkv = torch.randn(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    ms = _time_cuda(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, 2, HEADS, n, n), 3, 1)
+    q4 = qkv.view(2, n, 3, HEADS, 128)
+    qh, kh, vh = (q4[:, :, i].transpose(1, 2) for i in range(3))
+    ms_t = _time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh), 3, 1)
+    fl = 4 * 2 * HEADS * n * n * 128
+    res["self_attention"] = {"ours_ms": round(ms, 3), "sdpa_ms": round(ms_t, 3), "ours_tflops": round(fl / ms / 1e9, 1),
+                             "ours_over_sdpa": round(ms_t / ms, 3)}
+    return res
+
+
+VAE_TFLOP_A, VAE_MIN_BYTES_A = 180.5, 107.3e9  # SURVEY §8d: algorithmic FLOPs / minimum fused traffic of the decode @ 21x64x64
+
+
+def vae_decode_bench(dev, peaks):
+    """BASELINE.json config 5: Wan2.1 VAE decode of a [16,21,64,64] latent -> [3,81,512,512], random weights (seed 7)."""
+    from baseline import torchlib
+    from scail_b200.wan_vae import WanVAE
+    torch.manual_seed(7)
+    vae = WanVAE(dim=96, device=dev)
+    z = torch.randn(16, T_LAT, H_LAT, W_LAT, device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ms = min(_time_cuda(lambda: vae.decode([z]), 1, 1) for _ in range(3))
+        try:
+            ms_lib = min(_time_cuda(lambda: torchlib.vae_decode(vae, z), 1, 1) for _ in range(2))
+        except Exception as e:  # a library failure must not take the product's line down with it
+            ms_lib = None
+            lib_err = repr(e)[:200]
+    scale = (T_LAT * H_LAT * W_LAT) / (21 * 64 * 64)
+    tf = VAE_TFLOP_A * scale / ms * 1e3
+    out = {"workload": f"Wan2.1 VAE decode, latent {T_LAT}x{H_LAT}x{W_LAT} -> {4 * (T_LAT - 1) + 1} frames {8 * H_LAT}x{8 * W_LAT}",
+           "ms": ms, "tflops": tf, "frac_of_bf16_burst_peak": tf / peaks["bf16_tflops"],
+           "frac_of_bf16_sustained_peak": tf / peaks["bf16_tflops_sustained"], "algorithmic_tflop": VAE_TFLOP_A * scale,
+           "library_ms": ms_lib, "library": "F.conv3d bf16 channels_last_3d (cuDNN) + F.normalize/silu/interpolate (baseline/torchlib.py)",
+           "ours_over_library": (ms_lib / ms) if ms_lib else None}
+    if ms_lib is None:
+        out["library_error"] = lib_err
+    return out
+
+
+def cp_consistency_check(model, d, cond, uc, sig, rank, dist, layers=2):
+    """N > 1: the first `layers` blocks of step 0 computed (a) context-parallel over all ranks and (b) on rank 0 alone with
+    the single-GPU path; returns relL2 of (a) vs (b) on rank 0 (None elsewhere) so the scaling run carries correctness."""
+    from scail_b200 import sampler
+    ad = model.mixins["adaln_layer"]
+    x0 = d["x"].clone()
+    a = sampler.sampler_step(model, x0.clone(), sig[0], sig[1], cond, uc, 4.0, _num_layers=layers)
+    rel = None
+    if rank == 0:
+        cp, ad.cp = ad.cp, None
+        try:
+            b = sampler.sampler_step(model, x0.clone(), sig[0], sig[1], cond, uc, 4.0, _num_layers=layers)
+        finally:
+            ad.cp = cp
+        dsig = float(sig[1]) - float(sig[0])
+        va, vb = (a - x0) / dsig, (b - x0) / dsig
+        rel = float((va - vb).norm() / vb.norm())
+    dist.barrier()
+    return rel
 
 
 def workload_config(n_gpus):
@@ -196,7 +322,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torchlib"])
+    ap.add_argument("--no-extras", action="store_true", help="skip library_baseline / kernel_compare / vae_decode (profiling runs)")
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)  # debugging only; default = full model
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--latent", default=None, help="TxHxW latent override, e.g. 21x64x112 (the reference's default 512x896); "
@@ -235,11 +362,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    lib_arm = args.impl == "torchlib"
+    if lib_arm:
+        assert world == 1, "--impl torchlib is the single-GPU library baseline"
+        from baseline import torchlib
+
     def step(i):
         j = i % 50
-        sampler.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0)
+        if lib_arm:
+            x.copy_(torchlib.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0))
+        else:
+            sampler.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0)
 
+    cp_check = None
     with torch.no_grad():
+        if world > 1:
+            cp_check = cp_consistency_check(model, d, cond, uc, sig, rank, dist)
         for i in range(args.warmup):
             step(i)
         # ---- timed region: device-resident inputs ----
@@ -260,7 +398,7 @@ def main():
         attn_ms = [a.elapsed_time(b) for a, b in ops.ATTN_EVENTS]
         ops.ATTN_EVENTS = None
         # ---- e2e: host buffers through the public API ----
-        hs = sampler.HostStep(model, host, dev)
+        hs = sampler.HostStep(model, host, dev, step_fn=torchlib.sampler_step if lib_arm else None)
         hs(sig[0], sig[1])
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -306,9 +444,39 @@ def main():
                         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                         "algorithmic_flops_per_launch": attn_flops, "avg_launch_ms": attn_avg,
                         "share_of_step": sum(attn_ms) / args.steps / ms if attn_ms else None}}
+    out["latent_checksum"] = float(x.double().abs().mean())  # same seeded inputs => comparable across N and across arms
+    if cp_check is not None:
+        out["cp_check_rel"] = cp_check
     if args.layers != LAYERS:
         out["INVALID"] = f"debug run with {args.layers} layers"
-    if not args.no_cpu_baseline and world >= 1:
+    if lib_arm:
+        out["impl"] = "torchlib"
+        out["gpu_launches"] = 0
+        out["roofline"] = None
+        out["note"] = "PyTorch library path (cuBLASLt / flash-cuDNN SDPA / F.layer_norm), baseline/torchlib.py; none of this repo's kernels"
+    elif world == 1 and not args.no_extras:
+        from baseline import torchlib
+        with torch.no_grad():
+            xl = d["x"].clone()
+            fn = lambda: torchlib.sampler_step(model, xl, sig[10], sig[11], cond, uc, 4.0)
+            lib_ms = _time_cuda(fn, 2, 1)
+            # parity of the two arms on the bench's own inputs and weights: velocity of one step, ours vs library
+            xo = d["x"].clone()
+            sampler.sampler_step(model, xo, sig[10], sig[11], cond, uc, 4.0)
+            ref = fn()
+            dsig = float(sig[11]) - float(sig[10])
+            v_o, v_l = (xo - d["x"]) / dsig, (ref - d["x"]) / dsig
+            rel = float((v_o - v_l).norm() / v_l.norm())
+        out["library_baseline"] = {"steps_per_s": 1000.0 / lib_ms, "ms_per_step": lib_ms, "ours_over_library": lib_ms / ms,
+                                   "what": "the same step (weights, inputs, N, bf16) on the PyTorch library path the reference runs "
+                                           "on a GPU: F.linear (cuBLASLt), F.scaled_dot_product_attention, F.layer_norm; baseline/torchlib.py",
+                                   "guided_velocity_rel_l2_ours_vs_library": rel}
+        del xl, xo, ref
+        torch.cuda.empty_cache()
+        out["kernel_compare"] = kernel_compare(dev)
+        torch.cuda.empty_cache()
+        out["vae_decode"] = vae_decode_bench(dev, peaks)
+    if not args.no_cpu_baseline and world >= 1 and not lib_arm:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
 

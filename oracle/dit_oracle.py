@@ -162,9 +162,12 @@ def merge_heads(x):
     return x.permute(0, 2, 1, 3).reshape(b, n, h * d)
 
 
+USE_LIBRARY_SDPA = False  # bench.py's CPU-baseline leg sets this: full-N blocks cannot materialise the N x N scores
+
+
 def sdpa(q, k, v):
     """sat/transformer_defaults.py:67-72 (non-causal, scale 1/sqrt(d), no mask)."""
-    if q.dtype != torch.float32:  # "reference as shipped" mode: the library SDPA the reference calls
+    if USE_LIBRARY_SDPA or q.dtype != torch.float32:  # "reference as shipped" mode: the library SDPA the reference calls
         return F.scaled_dot_product_attention(q, k, v)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     return torch.softmax(s, -1) @ v

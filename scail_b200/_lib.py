@@ -9,7 +9,9 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscail_b200.so")
+# SCAIL_LIB_VARIANT=<tag> loads libscail_b200_<tag>.so instead (kernel A/B experiments under scripts/; never set in product use)
+_VARIANT = os.environ.get("SCAIL_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, f"libscail_b200_{_VARIANT}.so" if _VARIANT else "libscail_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -50,6 +52,8 @@ def sources():
 
 
 def needs_build():
+    if _VARIANT:
+        return False
     if not os.path.isfile(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

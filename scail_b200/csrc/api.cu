@@ -333,7 +333,7 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
     p.scale_log2 = scale * 1.4426950408889634f;
     p.accumulate = accumulate;
     p.trace = g_attn_trace;
-    static const int dbg = getenv("SCAIL_ATTN_DEBUG") ? atoi(getenv("SCAIL_ATTN_DEBUG")) : 0;
+    static const int dbg = getenv("SCAIL_ATTN_DEBUG") ? atoi(getenv("SCAIL_ATTN_DEBUG")) : 0;  // honoured only by -DSCAIL_ATTN_EXPERIMENTS builds
     p.debug = dbg;
     if ((rc = set_smem(attention_fwd_kernel, ATT_SMEM_BYTES))) return rc;
     dim3 grid(blocks_for(q_len, 2 * ATT_BQ), (unsigned)H, (unsigned)B);

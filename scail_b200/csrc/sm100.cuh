@@ -293,7 +293,8 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
 }
 // exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max rel err 7.5e-5):
 // relieves the MUFU pipe, which is co-critical with the tensor pipe in attention (16 ex2/clk/SM).
-__device__ __forceinline__ void poly_exp2_x2(uint64_t y2, float& e0, float& e1) {
+// Packed in, packed out: 6 FFMA2/FADD2 + 2 FMNMX + 2 IMAD per PAIR of exponentials.
+__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t y2) {
     float y0, y1;
     unpack_f32x2(y2, y0, y1);
     y2 = pack_f32x2(fmaxf(y0, -125.0f), fmaxf(y1, -125.0f));
@@ -308,9 +309,10 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t y2, float& e0, float& e1) 
     float p0, p1, t0, t1;
     unpack_f32x2(p2, p0, p1);
     unpack_f32x2(t2, t0, t1);
-    e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));         // scale by 2^round(y)
-    e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+    return pack_f32x2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),  // scale by 2^round(y)
+                      __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>

@@ -143,6 +143,24 @@ class _Workspace:
 _WS = _Workspace()
 
 
+class Conditioning:
+    """Step-invariant conditioning of one sample: text / CLIP embeddings and every layer's
+    cross-attention K,V, computed ONCE by `DiffusionTransformer.set_conditioning` with the same kernels the per-step path
+    uses (bit-identical).  It holds references to the caller's `context` / `image_clip_features` tensors and is used only
+    while forward() is called with those very tensor OBJECTS at the same `_version` — never matched by address, so a new
+    prompt living at a recycled address cannot hit a stale entry."""
+
+    def __init__(self, context, clip_feats, batch):
+        self.context, self.clip_feats, self.batch = context, clip_feats, batch
+        self.versions = (context._version, clip_feats._version)
+        self.text = self.clip = None
+        self.xkv = []  # per layer: (tkv [B*Lt, 2d], ckv [B*Lc, 2d])
+
+    def matches(self, context, clip_feats, batch):
+        return (context is self.context and clip_feats is self.clip_feats and batch == self.batch
+                and (context._version, clip_feats._version) == self.versions)
+
+
 def _need_cuda(t):
     if not t.is_cuda:
         raise RuntimeError("scail_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
@@ -291,10 +309,10 @@ class AdaLNMixin(BaseMixin):
         self.cp = None  # scail_b200.parallel.ContextParallel or None
         # text / CLIP K,V of every layer depend only on the prompt and the reference image,
         # yet the reference recomputes them in all 40 blocks of all 50 steps (dit_video_crossattn_sc_xc.py:1117-1130).
-        # With cache_cross_kv=True they are computed once per (context, clip) tensor pair and reused — numerically
-        # identical.  bench.py keeps it OFF so that the timed step does the reference's full work.
+        # With cache_cross_kv=True, sampler.sample() precomputes them once per call (DiffusionTransformer.set_conditioning,
+        # an explicit handle — nothing is keyed on tensor addresses) and every step reuses them: numerically identical.
+        # bench.py keeps it OFF so that the timed step does the reference's full work.
         self.cache_cross_kv = False
-        self._xkv_cache = {}
 
     # -- hooks ---------------------------------------------------------------------------------
     def layer_forward(self, hidden_states, mask, *args, **kwargs):
@@ -322,7 +340,9 @@ class AdaLNMixin(BaseMixin):
         # ---- cross attention (:1039-1042) ----
         pl = layer.post_cross_attention_layernorm
         ops.ln_modulate(x, out=lnb, gamma=pl.weight, beta=pl.bias, eps=eps)
+        xkv_all = kwargs.get("_xkv_layers")
         self.cross_attention_forward(lnb, kwargs.get("cross_attention_mask"), kwargs["encoder_outputs"], _ctx_out=ctx,
+                                     _xkv=xkv_all[l] if xkv_all is not None else None,
                                      **{k: v for k, v in kwargs.items() if k not in ("cross_attention_mask", "encoder_outputs")})
         c = layer.cross_attention
         ops.gemm(ctx, c.dense.weight, c.dense.bias, out=x2, epilogue=ops.EPI_BIAS_RES, residual=x2)
@@ -355,7 +375,10 @@ class AdaLNMixin(BaseMixin):
             ops.rmsnorm_rope(qkv, N, d, [(0, wq), (d, wk)], cos, sin, eps=self.layernorm_epsilon)
             ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, B, H, N, N)
         else:
-            self.cp.self_attention(self, a, h2, B, N, d, H, wq, wk, cos, sin, ctx)
+            # engine-style sequence parallelism (diffusion_video.py:495-552): the latents arrive pre-chunked on H or W, so the
+            # RoPE tables built from rope_H/W_shift are already this rank's; otherwise tokens were sharded by shard_tokens()
+            self.cp.self_attention(self, a, h2, B, N, d, H, wq, wk, cos, sin, ctx,
+                                   tables_local=kw_args.get("chunk_dim") is not None)
         if _ctx_out is not None:
             return None
         return ops.gemm(ctx, a.dense.weight, a.dense.bias).view(B, N, d)
@@ -375,27 +398,33 @@ class AdaLNMixin(BaseMixin):
         xq = _WS.get("xq", (B * N, d), dev)
         ops.gemm(hidden_states.view(B * N, d), c.query.weight, c.query.bias, out=xq)
         ops.rmsnorm_rope(xq, N, d, [(0, self.cross_query_layernorm_list[l].weight)], eps=eps)
-        ckey = (l, text.data_ptr(), text._version, tuple(text.shape), clip.data_ptr(), clip._version, tuple(clip.shape))
-        cached = self._xkv_cache.get(l) if self.cache_cross_kv else None
-        if cached is not None and cached[0] == ckey:
-            tkv, ckv = cached[1], cached[2]
+        pre = kw_args.get("_xkv")  # (tkv, ckv) of this layer from a Conditioning handle (rows of this call's batch elements)
+        if pre is not None:
+            tkv, ckv = pre
         else:
-            keep = self.cache_cross_kv
-            tkv = torch.empty(B * Lt, 2 * d, device=dev, dtype=bf) if keep else _WS.get("tkv", (B * Lt, 2 * d), dev)
-            ops.gemm(text.view(B * Lt, d), c.key_value.weight, c.key_value.bias, out=tkv)
-            ops.rmsnorm_rope(tkv, Lt, d, [(0, self.cross_key_layernorm_list[l].weight)], eps=eps)
-            ckv_lin = self.clip_feature_key_value_list[l]
-            ckv = torch.empty(B * Lc, 2 * d, device=dev, dtype=bf) if keep else _WS.get("ckv", (B * Lc, 2 * d), dev)
-            ops.gemm(clip.view(B * Lc, d), ckv_lin.weight, ckv_lin.bias, out=ckv)
-            ops.rmsnorm_rope(ckv, Lc, d, [(0, self.clip_feature_key_layernorm_list[l].weight)], eps=eps)
-            if keep:
-                self._xkv_cache[l] = (ckey, tkv, ckv)
+            tkv, ckv = self.cross_kv(l, text, clip)
         ctx = _ctx_out if _ctx_out is not None else torch.empty(B * N, d, device=dev, dtype=bf)
         ops.attention(xq, tkv[:, :d], tkv[:, d:], ctx, B, H, N, Lt)
         ops.attention(xq, ckv[:, :d], ckv[:, d:], ctx, B, H, N, Lc, accumulate=True)
         if _ctx_out is not None:
             return None
         return ops.gemm(ctx, c.dense.weight, c.dense.bias).view(B, N, d)
+
+    def cross_kv(self, l, text, clip, keep=False):
+        """Text and CLIP K,V of layer l (:1117-1130): K/V projection + K RMSNorm.  keep=True allocates fresh buffers (for a
+        Conditioning handle) instead of the per-stream workspace."""
+        c = self.transformer.layers[l].cross_attention
+        B, Lt, d = text.shape
+        Lc = clip.shape[1]
+        dev, bf, eps = text.device, torch.bfloat16, self.layernorm_epsilon
+        tkv = torch.empty(B * Lt, 2 * d, device=dev, dtype=bf) if keep else _WS.get("tkv", (B * Lt, 2 * d), dev)
+        ops.gemm(text.view(B * Lt, d), c.key_value.weight, c.key_value.bias, out=tkv)
+        ops.rmsnorm_rope(tkv, Lt, d, [(0, self.cross_key_layernorm_list[l].weight)], eps=eps)
+        ckv_lin = self.clip_feature_key_value_list[l]
+        ckv = torch.empty(B * Lc, 2 * d, device=dev, dtype=bf) if keep else _WS.get("ckv", (B * Lc, 2 * d), dev)
+        ops.gemm(clip.view(B * Lc, d), ckv_lin.weight, ckv_lin.bias, out=ckv)
+        ops.rmsnorm_rope(ckv, Lc, d, [(0, self.clip_feature_key_layernorm_list[l].weight)], eps=eps)
+        return tkv, ckv
 
     def _rope_tables(self, dev, **kw):
         pe = getattr(self, "_pos_embed", None)
@@ -473,31 +502,49 @@ class DiffusionTransformer(nn.Module):
         return self.mixins[name]
 
     # -- per-step embeddings (dit_video_crossattn_sc_xc.py:1505-1555) -----------------------------
-    def _embeddings(self, timesteps, context, clip_feats, B):
+    def _text_clip_embeddings(self, context, clip_feats, B):
+        """text_embedding (:1505) and clip_proj (:1507-1515): depend on the prompt / reference image only."""
         bf = torch.bfloat16
         dev = context.device
         d = self.hidden_size
+        te = self.text_embedding
+        Lt = context.shape[1]
+        c2 = context.to(bf).contiguous().view(-1, self.text_dim)
+        t1 = ops.gemm(c2, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
+        text = ops.gemm(t1, te[2].weight, te[2].bias).view(context.shape[0], Lt, d)
+        p = self.clip_proj.proj
+        cf = clip_feats.to(device=dev, dtype=bf).contiguous()
+        Bc, Lc, dc = cf.shape
+        c0 = ops.ln_modulate(cf, gamma=p[0].weight, beta=p[0].bias, eps=p[0].eps)
+        c1 = ops.gemm(c0.view(Bc * Lc, dc), p[1].weight, p[1].bias, epilogue=ops.EPI_BIAS_GELU_ERF)
+        c3 = ops.gemm(c1, p[3].weight, p[3].bias).view(Bc, Lc, d)
+        clip = ops.ln_modulate(c3, gamma=p[4].weight, beta=p[4].bias, eps=p[4].eps)
+        if Bc != B:
+            clip = clip.repeat(B // Bc, 1, 1)  # :1512-1515
+        return text, clip
+
+    def set_conditioning(self, context, image_clip_features, batch=None):
+        """Precompute the step-invariant conditioning for `context` [b,L,text_dim] / `image_clip_features` [1|b,257,1280]
+        (SURVEY §8f rank 1).  Subsequent forward() calls that pass these SAME tensor objects skip text_embedding, clip_proj
+        and all 40 layers' text/CLIP K,V projections.  Returns the handle; clear_conditioning() drops it."""
+        _need_cuda(context)
+        B = batch if batch is not None else context.shape[0]
+        cond = Conditioning(context, image_clip_features, B)
+        cond.text, cond.clip = self._text_clip_embeddings(context, image_clip_features, B)
         ad = self.mixins["adaln_layer"]
-        ekey = (context.data_ptr(), context._version, tuple(context.shape), clip_feats.data_ptr(), clip_feats._version, B)
-        if ad.cache_cross_kv and getattr(self, "_emb_cache", (None,))[0] == ekey:
-            text, clip = self._emb_cache[1], self._emb_cache[2]
+        cond.xkv = [ad.cross_kv(l, cond.text, cond.clip, keep=True) for l in range(self.num_layers)]
+        self._conditioning = cond
+        return cond
+
+    def clear_conditioning(self):
+        self._conditioning = None
+
+    def _embeddings(self, timesteps, context, clip_feats, B, cond=None):
+        dev = context.device
+        if cond is not None:
+            text, clip = cond.text, cond.clip
         else:
-            te = self.text_embedding
-            Lt = context.shape[1]
-            c2 = context.to(bf).contiguous().view(-1, self.text_dim)
-            t1 = ops.gemm(c2, te[0].weight, te[0].bias, epilogue=ops.EPI_BIAS_GELU)
-            text = ops.gemm(t1, te[2].weight, te[2].bias).view(context.shape[0], Lt, d)
-            p = self.clip_proj.proj
-            cf = clip_feats.to(device=dev, dtype=bf).contiguous()
-            Bc, Lc, dc = cf.shape
-            c0 = ops.ln_modulate(cf, gamma=p[0].weight, beta=p[0].bias, eps=p[0].eps)
-            c1 = ops.gemm(c0.view(Bc * Lc, dc), p[1].weight, p[1].bias, epilogue=ops.EPI_BIAS_GELU_ERF)
-            c3 = ops.gemm(c1, p[3].weight, p[3].bias).view(Bc, Lc, d)
-            clip = ops.ln_modulate(c3, gamma=p[4].weight, beta=p[4].bias, eps=p[4].eps)
-            if Bc != B:
-                clip = clip.repeat(B // Bc, 1, 1)  # :1512-1515
-            if ad.cache_cross_kv:
-                self._emb_cache = (ekey, text, clip)
+            text, clip = self._text_clip_embeddings(context, clip_feats, B)
         t_emb = ops.timestep_embedding(timesteps.to(device=dev, dtype=torch.float32).contiguous(), self.time_freq_dim)
         e1 = ops.gemm(t_emb, self.time_embed[0].weight, self.time_embed[0].bias, epilogue=ops.EPI_BIAS_SILU)
         emb = ops.gemm(e1, self.time_embed[2].weight, self.time_embed[2].bias)
@@ -506,7 +553,9 @@ class DiffusionTransformer(nn.Module):
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """x [b,t,16,h,w]; kwargs: ref_concat [1|b,1,16,h,w], concat_smpl_render [1|b,t,16,h/2,w/2],
-        image_clip_features [1|b,257,1280], concat_images (gate only, F12).  Returns [b,t,16,h,w] bf16."""
+        image_clip_features [1|b,257,1280], concat_images (gate only, F12), history_mask [1|b,t,4,h,w] (optional: the mask
+        channels of x, :1462-1467), chunk_dim (3 | 4 | None: the engine's pre-chunked sequence parallelism,
+        diffusion_video.py:495-552).  Returns [b,t,16,h,w] bf16 (the local chunk when chunk_dim is set)."""
         _need_cuda(x)
         assert y is None, "SCAIL's DiT is not class-conditional (num_classes is None)"
         assert kwargs.get("ref_concat") is not None, "must specify ref_concat"
@@ -515,38 +564,67 @@ class DiffusionTransformer(nn.Module):
         xb = ops.cast_bf16(x.contiguous()) if x.dtype == torch.float32 else x.to(bf).contiguous()
         ref = kwargs["ref_concat"].to(bf).contiguous()
         pose = kwargs["concat_smpl_render"].to(bf).contiguous()
-        text, clip, emb, adaln = self._embeddings(timesteps, context, kwargs["image_clip_features"], b)
+        hm = kwargs.get("history_mask")
+        if hm is not None:
+            # non-zero mask channels: assemble the 20-channel inputs explicitly, exactly as :1462-1503 does
+            rep = lambda a: a.to(bf).repeat(b // a.shape[0], 1, 1, 1, 1)
+            xb = torch.cat([xb, rep(hm)], 2).contiguous()
+            ref = torch.cat([rep(ref), torch.ones(b, 1, 4, h, w, device=x.device, dtype=bf)], 2).contiguous()
+            pose = torch.cat([rep(pose), torch.ones(b, t, 4, h // 2, w // 2, device=x.device, dtype=bf)], 2).contiguous()
+        cond = getattr(self, "_conditioning", None)
+        if cond is not None and not cond.matches(context, kwargs["image_clip_features"], b):
+            cond = None  # different prompt / image tensors: compute everything (never reuse by address)
+        text, clip, emb, adaln = self._embeddings(timesteps, context, kwargs["image_clip_features"], b, cond)
         pp = reduce(mul, self.patch_size)
         kw = dict(seq_length=t * h * w // pp, pose_length=t * (h // 2) * (w // 2) // pp, ref_length=h * w // pp,
                   emb=adaln, final_layer_emb=emb, encoder_outputs=text, image_clip_features=clip,
                   cross_attention_mask=None, rope_T=t // self.patch_size[0], rope_H=h // self.patch_size[1],
-                  rope_W=w // self.patch_size[2], global_rope_H=0, global_rope_W=120, rope_H_shift=0, rope_W_shift=0)
+                  rope_W=w // self.patch_size[2], global_rope_H=0, global_rope_W=120, rope_H_shift=0, rope_W_shift=0,
+                  _xkv_layers=cond.xkv if cond is not None else None)
+        ad = self.mixins["adaln_layer"]
+        cp = ad.cp
+        chunk_dim = kwargs.get("chunk_dim")
+        if chunk_dim is not None:  # :1578-1585
+            if cp is None or cp.size == 1:
+                raise RuntimeError("chunk_dim is set but no ContextParallel group is attached (adaln_layer.cp)")
+            if chunk_dim == 3:
+                kw["rope_H_shift"] = cp.rank * kw["rope_H"]
+            elif chunk_dim == 4:
+                kw["rope_W_shift"] = cp.rank * kw["rope_W"]
+            else:
+                raise NotImplementedError("chunk_dim must be 3 (H) or 4 (W)")
+            kw["chunk_dim"] = chunk_dim
         N = kw["ref_length"] + kw["seq_length"] + kw["pose_length"]
         hidden = _WS.get("hidden", (b, N, self.hidden_size), x.device)
         # the 16-channel inputs go straight to the gather kernel, which synthesises the mask channels
         hidden = self.mixins["patch_embed"].word_embedding_forward(None, images=xb, ref_concat=ref,
                                                                    concat_smpl_render=pose, _hidden_out=hidden)
-        cp = self.mixins["adaln_layer"].cp
-        ad = self.mixins["adaln_layer"]
+        n_layers = int(kwargs.get("_num_layers") or self.num_layers)  # verification hook (bench.py cp_check_rel): first k blocks only
         if cp is None or cp.size == 1:
-            for l in range(self.num_layers):
+            for l in range(n_layers):
                 hidden = ad.layer_forward(hidden, None, layer_id=l, **kw)
             return self.mixins["final_layer"].final_forward(hidden, **kw)
-        # ---- context parallel: token shard; the CFG branches (independent batch elements) run on separate
-        # streams so that one branch's K/V all-gather overlaps the other branch's GEMMs / attention ----
-        local = cp.shard_tokens(hidden)
+        # ---- context parallel: the CFG branches (independent batch elements) run on separate streams so that one
+        # branch's K/V all-gather overlaps the other branch's GEMMs / attention.  Tokens are either sharded here
+        # (replicated inputs) or already local (chunk_dim: the engine chunked the latents on H/W per rank) ----
+        local = hidden if chunk_dim is not None else cp.shard_tokens(hidden)
         main = torch.cuda.current_stream()
         streams = cp.branch_streams(b, x.device)
         per = []
         for i in range(b):
             kwi = dict(kw, emb=adaln[i:i + 1], encoder_outputs=text[i:i + 1], image_clip_features=clip[i:i + 1])
+            if cond is not None:
+                Lt, Lc = text.shape[1], clip.shape[1]
+                kwi["_xkv_layers"] = [(tk[i * Lt:(i + 1) * Lt], ck[i * Lc:(i + 1) * Lc]) for tk, ck in cond.xkv]
             per.append([local[i:i + 1].contiguous(), kwi])
             streams[i].wait_stream(main)
-        for l in range(self.num_layers):
+        for l in range(n_layers):
             for i in range(b):
                 with torch.cuda.stream(streams[i]):
                     per[i][0] = ad.layer_forward(per[i][0], None, layer_id=l, **per[i][1])
         for i in range(b):
             main.wait_stream(streams[i])
-        hidden = cp.gather_tokens(torch.cat([h for h, _ in per], 0), N)
+        hidden = torch.cat([h_ for h_, _ in per], 0)
+        if chunk_dim is None:
+            hidden = cp.gather_tokens(hidden, N)
         return self.mixins["final_layer"].final_forward(hidden, **kw)

@@ -70,11 +70,22 @@ class ContextParallel:
         return works
 
     # ---- the block's self-attention under CP (kernels) ----
-    def self_attention(self, mixin, attn, h2, B, n_local, d, H, wq, wk, cos, sin, ctx):
+    def self_attention(self, mixin, attn, h2, B, n_local, d, H, wq, wk, cos, sin, ctx, tables_local=False):
+        """tables_local: cos/sin already describe this rank's tokens (engine-style pre-chunked latents whose RoPE offsets
+        come from rope_H/W_shift); otherwise they cover the full sequence and this rank's contiguous slice is taken.
+        Keys/values are gathered in rank order either way (softmax is order-free)."""
         dev = h2.device
         P = self.size
         eps = mixin.layernorm_epsilon
-        cos_l, sin_l = self.rope_slice(cos, sin, n_local)
+        if tables_local:
+            if cos.shape[0] != n_local:
+                raise ValueError(f"pre-chunked context parallelism: RoPE tables have {cos.shape[0]} rows for {n_local} local tokens")
+            cos_l, sin_l = cos, sin
+        else:
+            if cos.shape[0] != P * n_local:
+                raise ValueError(f"context parallelism: RoPE tables have {cos.shape[0]} rows but P * n_local = {P} * {n_local}; "
+                                 "tokens must be sharded with shard_tokens() (or pass chunk_dim for pre-chunked latents)")
+            cos_l, sin_l = self.rope_slice(cos, sin, n_local)
         w, bias = attn.query_key_value.weight, attn.query_key_value.bias
         kvbuf = self.kv_buffer(B, n_local, d, dev)
         for b in range(B):  # K,V projection straight into this rank's slot of the gather buffer

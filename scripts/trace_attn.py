@@ -1,6 +1,6 @@
-"""Per-iteration clock64 trace of attention CTA (0,0,0).  Needs the experiment hooks compiled in:
-    SCAIL_NVCC_EXTRA=-DSCAIL_ATTN_EXPERIMENTS python -c "from scail_b200 import _lib; _lib.build(force=True)"
-(ablation modes: SCAIL_ATTN_DEBUG=1 softmax skipped, 2 MMA ignores P barriers, 3 TMEM read only, 5 PV only, 6 QK only)."""
+"""Per-substep clock64 trace of attention CTA (0,0,0).  Needs the experiment hooks compiled in
+(-DSCAIL_ATTN_EXPERIMENTS; scripts/build_variants.sh builds libscail_b200_v2x.so; run with SCAIL_LIB_VARIANT=v2x).
+Ablation modes: SCAIL_ATTN_DEBUG=1 softmax skipped, 5 no QK^T UMMAs, 6 no PV UMMAs."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from scail_b200 import ops, _lib
@@ -14,10 +14,9 @@ _lib.lib().scail_debug_set_attention_trace(tr.data_ptr())
 f(); torch.cuda.synchronize()
 _lib.lib().scail_debug_set_attention_trace(None)
 t = tr.view(64, 8).cpu()
-base = int(t[8, 0])
-print("j: mma_wait0_start  wait0_end(+dt)  s0_commit_issued  wait1_end | softmax0: wait_start  wake")
-for j in range(8, 24):
-    r = [int(x) - base for x in t[j]]
-    print(j, r[0], r[1], "(+%d)" % (r[1] - r[0]), r[2], r[3], "|", r[4], r[5], "(+%d)" % (r[5] - r[4]))
-per = (int(t[40, 0]) - int(t[8, 0])) / 32
-print("cycles per kv step:", per)
+base = int(t[16, 0])
+print("s: MMA: P(t0) wait start, end(+dt) | P(t1) wait start, end(+dt) || softmax0: S wait start, wake(+dt)")
+for s in range(16, 40):
+    r = [int(x) - base for x in t[s]]
+    print(s, r[0], "(+%d)" % (r[1] - r[0]), "|", r[2], "(+%d)" % (r[3] - r[2]), "||", r[4], "(+%d)" % (r[5] - r[4]))
+print("cycles per 128-key step:", 2 * (int(t[56, 0]) - int(t[16, 0])) / 40)

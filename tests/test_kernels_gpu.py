@@ -115,7 +115,8 @@ def test_rmsnorm_rope(D, heads):
 
 
 @pytest.mark.parametrize("B,H,nq,nkv", [(1, 1, 256, 128), (1, 2, 256, 256), (2, 2, 384, 384), (1, 2, 300, 257),
-                                        (2, 3, 512, 1000), (1, 1, 128, 4096)])
+                                        (2, 3, 512, 1000), (1, 1, 128, 4096), (1, 1, 128, 64), (1, 2, 256, 40),
+                                        (1, 1, 256, 191), (2, 1, 130, 193), (1, 2, 256, 320)])
 def test_attention(B, H, nq, nkv):
     from oracle import dit_oracle as O
     from scail_b200 import ops
