@@ -278,7 +278,7 @@ int scail_ln_modulate(const void* x, void* out, const void* gamma, const void* b
                       int64_t in_row_offset, int64_t D, float eps, scail_stream_t stream) {
     using namespace scail;
     SCAIL_REQUIRE(x && out, "ln_modulate: null operand");
-    SCAIL_REQUIRE(D % 256 == 0 && D <= ROW_MAXV * 256, "ln_modulate: D=%lld must be a multiple of 256 and <= %d", (long long)D, ROW_MAXV * 256);
+    SCAIL_REQUIRE(D % 8 == 0 && D <= ROW_MAXV * ROW_THREADS * 8, "ln_modulate: D=%lld must be a multiple of 8 and <= %d", (long long)D, ROW_MAXV * ROW_THREADS * 8);
     SCAIL_REQUIRE((gamma == nullptr) == (beta == nullptr) && (shift == nullptr) == (scale == nullptr), "ln_modulate: gamma/beta and shift/scale come in pairs");
     LnModParams p;
     p.x = static_cast<const __nv_bfloat16*>(x); p.out = static_cast<__nv_bfloat16*>(out);
@@ -286,7 +286,7 @@ int scail_ln_modulate(const void* x, void* out, const void* gamma, const void* b
     p.shift = static_cast<const __nv_bfloat16*>(shift); p.scale = static_cast<const __nv_bfloat16*>(scale);
     p.mod_stride = mod_stride; p.D = (int)D; p.rows_out = (int)rows_out; p.in_batch_rows = (int)in_batch_rows;
     p.in_row_offset = (int)in_row_offset; p.total_rows = (int)(B * rows_out); p.eps = eps;
-    ln_modulate_kernel<<<blocks_for(p.total_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ln_modulate_kernel<<<p.total_rows, ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
     SCAIL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -296,7 +296,9 @@ int scail_rmsnorm_rope(void* buf, int64_t ld, int64_t rows, int64_t rows_per_bat
                        const float* cos, const float* sin, float eps, scail_stream_t stream) {
     using namespace scail;
     SCAIL_REQUIRE(buf && weight0 && (nslabs == 1 || (nslabs == 2 && weight1)), "rmsnorm_rope: null operand");
-    SCAIL_REQUIRE(D % 256 == 0 && D <= ROW_MAXV * 256 && ld % 8 == 0 && col_offset0 % 8 == 0 && col_offset1 % 8 == 0, "rmsnorm_rope: bad D/ld/offset");
+    SCAIL_REQUIRE(D % 8 == 0 && D <= ROW_MAXV * ROW_THREADS * 8 && ld % 8 == 0 && col_offset0 % 8 == 0 && col_offset1 % 8 == 0, "rmsnorm_rope: bad D/ld/offset");
+    SCAIL_REQUIRE(!cos || D % 128 == 0, "rmsnorm_rope: RoPE needs D to be a multiple of the 128-wide head");
+    SCAIL_REQUIRE(rows > 0 && rows_per_batch > 0, "rmsnorm_rope: bad row counts");
     SCAIL_REQUIRE((cos == nullptr) == (sin == nullptr), "rmsnorm_rope: cos/sin come in pairs");
     RmsRopeParams p;
     p.buf = static_cast<__nv_bfloat16*>(buf); p.ld = ld;
@@ -304,8 +306,8 @@ int scail_rmsnorm_rope(void* buf, int64_t ld, int64_t rows, int64_t rows_per_bat
     p.weight[0] = static_cast<const __nv_bfloat16*>(weight0); p.weight[1] = static_cast<const __nv_bfloat16*>(weight1);
     p.nslabs = nslabs; p.D = (int)D; p.rows = (int)rows; p.rows_per_batch = (int)rows_per_batch;
     p.cos = cos; p.sin = sin; p.eps = eps;
-    dim3 grid(blocks_for(rows, 8), nslabs);
-    rmsnorm_rope_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    dim3 grid((unsigned)rows, nslabs);
+    rmsnorm_rope_kernel<<<grid, ROW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
     SCAIL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

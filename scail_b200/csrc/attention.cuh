@@ -10,24 +10,27 @@
 // The MMA warp keeps its control flow warp-uniform (all lanes wait on the mbarriers; descriptors are computed in
 // uniform registers) and only the tcgen05 instructions are issued by the elected lane.
 //
-// Pipeline granularity is a 64-key HALF of a 128-key K/V tile ("substep").  TMEM (512 columns):
-//   S0 = [S0.lo | S0.hi] | S1 = [S1.lo | S1.hi] | O0 | O1        (64 + 64 | 64 + 64 | 128 | 128 fp32 columns)
-// S(t, half) = Q_t K[half]^T is a 128x64x16 UMMA chain; P(t, half) (bf16, 32 columns) aliases the first half of ITS OWN
-// S half and feeds O_t += P V[half] as the TMEM A operand.  Because the two halves of a Q tile's score buffer are
-// independent, the next QK^T of a half is issued as soon as the PV of that half has been issued -- while the softmax
-// warpgroup is busy with the OTHER half -- so the chain  S -> softmax -> P -> PV -> next S  (which used to serialise a
-// whole 128-key tile: ~3200 cycles per KV step against 2048 cycles of UMMA work) no longer gates the tensor pipe: the
-// softmax warpgroups always find their next half ready and the kernel is bound by max(UMMA, MUFU/FMA throughput).
-// A fraction of the exponentials (ATT_POLY_MASK) runs as a Cody-Waite + cubic polynomial on the FMA pipe, since MUFU.EX2
-// (16/clk/SM) would otherwise need exactly as many cycles as the UMMAs.
-// Online softmax keeps a (possibly stale) running max; O is rescaled only when the max grew by > 2^8, after waiting for
-// the previous PV of that tile (B_ODONE) so the read-modify-write of O cannot race the tensor core.
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P (bf16) aliases the first 64 columns of its S buffer and
+// feeds the PV product as the TMEM A operand (no smem round trip).
+//   S = Q K^T : UMMA 128x128x16, A/B K-major from smem (TMA SWIZZLE_128B) -- measured (scripts/umma_microbench.cu): this shape
+//               reads 8 KB of operands per 64-cycle UMMA = exactly the 128 B/clk/SM shared-memory operand bandwidth; the
+//               N = 64 variant is operand-bound at 48 instead of 32 cycles, which is why S is NOT split into halves.
+//   O += P V  : UMMA 128x128x16, A from TMEM, B = V tile read MN-major straight from its [kv, d] layout (full rate).
+// Because P aliases S, one Q tile's loop-carried chain is  S -> softmax -> P -> PV -> next QK^T -> S, and the step time is
+// max(2048 cycles of UMMA, softmax latency + the part of PV + QK^T that cannot start before the last P column exists).
+// Two things shorten that chain:
+//   * P is handed over in ATT_P_SPLIT column groups with one mbarrier each, so the PV UMMAs of the first groups run while
+//     the later exponentials are still being computed (only the last group's k-steps stay on the chain);
+//   * a fraction of the exponentials (ATT_POLY_MASK) runs as a Cody-Waite + cubic polynomial on the FMA pipe: MUFU.EX2
+//     (16/clk/SM) alone needs 1024 cycles per 128x128 tile.
+// Online softmax keeps a (possibly stale) running max; O is rescaled only when the max grew by > 2^8 (S full implies the
+// previous PV of that tile has completed, so the read-modify-write of O cannot race the tensor core).
 #pragma once
 #include "sm100.cuh"
 
 #ifdef SCAIL_ATTN_EXPERIMENTS
 #define SCAIL_ATTN_TRACE(IDX) if (tr) p.trace[IDX] = clock64()
-#define SCAIL_ATTN_TRACE_DECL_MMA const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < 64 && leader;
+#define SCAIL_ATTN_TRACE_DECL_MMA
 #else
 #define SCAIL_ATTN_TRACE(IDX)
 #define SCAIL_ATTN_TRACE_DECL_MMA
@@ -39,21 +42,25 @@
 #ifndef SCAIL_ATT_K_STAGES
 #define SCAIL_ATT_K_STAGES 3
 #endif
+#ifndef SCAIL_ATT_P_SPLIT
+#define SCAIL_ATT_P_SPLIT 4  // P hand-over groups per tile (1, 2 or 4): group g covers 128 / SPLIT keys
+#endif
 
 namespace scail {
 
 constexpr int ATT_D = 128;
 constexpr int ATT_BQ = 128;   // rows per Q tile (2 tiles per CTA)
-constexpr int ATT_BKV = 128;  // keys per TMA tile
-constexpr int ATT_SUB = 64;   // keys per pipeline substep (half a tile)
+constexpr int ATT_BKV = 128;  // keys per K/V tile
 constexpr int ATT_K_STAGES = SCAIL_ATT_K_STAGES;
 constexpr int ATT_V_STAGES = 2;
+constexpr int ATT_P_SPLIT = SCAIL_ATT_P_SPLIT;
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: one 128x128 bf16 tile (two 64-column halves)
 constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
 constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle warps}
 constexpr uint32_t ATT_POLY_MASK = SCAIL_ATT_POLY_MASK;
 constexpr int ATT_SMEM_BYTES = (2 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 static_assert(ATT_SMEM_BYTES <= 232448, "attention: shared memory budget");
+static_assert(ATT_P_SPLIT == 1 || ATT_P_SPLIT == 2 || ATT_P_SPLIT == 4, "attention: P split");
 
 struct AttnParams {
     __nv_bfloat16* out;  // [B*q_rows_per_batch, ldo]; head h written at columns [h*128, h*128+128)
@@ -64,44 +71,69 @@ struct AttnParams {
     int kv_batch_rows;   // row stride between batches in the K/V matrices
     float scale_log2;    // softmax scale * log2(e)
     int accumulate;      // out += result (second cross-attention pass, dit_video_crossattn_sc_xc.py:1197)
-    long long* trace;    // perf experiments only: per-substep clock64 stamps of CTA (0,0,0), or null
+    long long* trace;    // perf experiments only: per-step clock64 stamps of CTA (0,0,0), or null
     int debug;           // perf experiments only (SCAIL_ATTN_DEBUG): 1 = softmax skips its math, 5 = no QK^T UMMAs, 6 = no PV UMMAs
 };
 
-// One 128x64 score half of one softmax warp (thread = row): TMEM S -> running max (lazy O rescale) -> exp2 ->
-// bf16 P back into TMEM (first 32 columns of the same half).  MASK = this is the partial last substep.
+// exp2 of one 32-column chunk (16 packed pairs) -> 16 packed bf16x2 words of P; pairs selected by ATT_POLY_MASK use the
+// FMA-pipe polynomial, the others MUFU.EX2.  Row sums accumulate in two packed fp32 pairs.
+__device__ __forceinline__ void exp_chunk(const uint32_t (&src)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum_a, uint64_t& sum_b,
+                                          uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const uint64_t y2 = fma_f32x2(pack_f32x2(__uint_as_float(src[2 * c]), __uint_as_float(src[2 * c + 1])), sc2, nm2);
+        uint64_t e2;
+        if ((ATT_POLY_MASK >> c) & 1u) {
+            e2 = poly_exp2_x2(y2);
+        } else {
+            float y0, y1;
+            unpack_f32x2(y2, y0, y1);
+            e2 = pack_f32x2(fast_exp2(y0), fast_exp2(y1));
+        }
+        if (c & 1) sum_b = add_f32x2(sum_b, e2);
+        else sum_a = add_f32x2(sum_a, e2);
+        float e0, e1;
+        unpack_f32x2(e2, e0, e1);
+        pk[c] = pack_bf16(e0, e1);
+    }
+}
+
+// One 128x128 score tile of one softmax warp (thread = row): TMEM S -> running max (lazy O rescale) -> exp2 ->
+// bf16 P back into TMEM, handed to the MMA warp in ATT_P_SPLIT groups.  MASK = this is the partial last KV tile.
 template <bool MASK>
-__device__ __forceinline__ void softmax_half(uint32_t s_tmem, uint32_t o_tmem, float scale_log2, int valid, int sidx,
-                                             float& m_run, float& l_run, uint32_t bar_pfull, uint32_t bar_odone) {
-    uint32_t sa[32], sb[32];
-    tmem_ld_32x32(s_tmem + 0, sa);
-    tmem_ld_32x32(s_tmem + 32, sb);
+__device__ __forceinline__ void softmax_tile(uint32_t s_tmem, uint32_t o_tmem, float scale_log2, int valid, int j,
+                                             float& m_run, float& l_run, uint32_t bar_pfull0) {
+    uint32_t s0[32], s1[32], s2[32], s3[32];
+    tmem_ld_32x32(s_tmem + 0, s0);
+    tmem_ld_32x32(s_tmem + 32, s1);
+    tmem_ld_32x32(s_tmem + 64, s2);
+    tmem_ld_32x32(s_tmem + 96, s3);
     tmem_ld_wait();
     if constexpr (MASK) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-            if (c >= valid) sa[c] = 0xff800000u;
-            if (c + 32 >= valid) sb[c] = 0xff800000u;
+            if (c >= valid) s0[c] = 0xff800000u;
+            if (c + 32 >= valid) s1[c] = 0xff800000u;
+            if (c + 64 >= valid) s2[c] = 0xff800000u;
+            if (c + 96 >= valid) s3[c] = 0xff800000u;
         }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(sa[c]), __uint_as_float(sa[c + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(sa[c + 2]), __uint_as_float(sa[c + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(sb[c]), __uint_as_float(sb[c + 1]));
-        mx3 = fmax3(mx3, __uint_as_float(sb[c + 2]), __uint_as_float(sb[c + 3]));
+    for (int c = 0; c < 32; c += 2) {
+        mx0 = fmax3(mx0, __uint_as_float(s0[c]), __uint_as_float(s0[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s1[c]), __uint_as_float(s1[c + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(s2[c]), __uint_as_float(s2[c + 1]));
+        mx3 = fmax3(mx3, __uint_as_float(s3[c]), __uint_as_float(s3[c + 1]));
     }
     const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     const float m_new = fmaxf(m_run, mx * scale_log2);
-    const bool need = (m_new - m_run) > 8.0f;  // also true on the first substep (m_run = -inf)
+    const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
     if (__any_sync(0xffffffffu, need)) {
-        const float alpha = fast_exp2(m_run - m_new);  // 0 on the first substep
+        const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
         m_run = m_new;
         l_run *= alpha;
-        if (sidx > 0) {
-            mbar_wait(bar_odone, (sidx - 1) & 1, 50);  // PV of the previous substep has landed in O
-            tc_fence_after();
+        if (j > 0) {
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t o[32];
@@ -116,38 +148,29 @@ __device__ __forceinline__ void softmax_half(uint32_t s_tmem, uint32_t o_tmem, f
     const float neg_m = -m_run;
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
     uint64_t sum_a = 0ull, sum_b = 0ull;  // packed (0.f, 0.f)
-#define SCAIL_ATT_P_CHUNK(SRC, CH)                                                                                  \
-    {                                                                                                               \
-        uint32_t pk[16];                                                                                            \
-        _Pragma("unroll") for (int c = 0; c < 16; ++c) {                                                            \
-            const uint64_t y2 = fma_f32x2(pack_f32x2(__uint_as_float(SRC[2 * c]), __uint_as_float(SRC[2 * c + 1])), sc2, nm2); \
-            uint64_t e2;                                                                                            \
-            if ((ATT_POLY_MASK >> c) & 1u) {                                                                        \
-                e2 = poly_exp2_x2(y2);                                                                              \
-            } else {                                                                                                \
-                float y0, y1;                                                                                       \
-                unpack_f32x2(y2, y0, y1);                                                                           \
-                e2 = pack_f32x2(fast_exp2(y0), fast_exp2(y1));                                                      \
-            }                                                                                                       \
-            if (c & 1) sum_b = add_f32x2(sum_b, e2);                                                                \
-            else sum_a = add_f32x2(sum_a, e2);                                                                      \
-            float e0, e1;                                                                                           \
-            unpack_f32x2(e2, e0, e1);                                                                               \
-            pk[c] = pack_bf16(e0, e1);                                                                              \
-        }                                                                                                           \
-        tmem_st_32x16(s_tmem + (CH) * 16, pk);                                                                      \
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    // chunk CH = 32 keys = 16 packed P columns; after the last chunk of hand-over group g the warp arrives on bar_pfull0 + 8 * g
+#define SCAIL_ATT_P_CHUNK(SRC, CH)                                             \
+    {                                                                          \
+        uint32_t pk[16];                                                       \
+        exp_chunk(SRC, sc2, nm2, sum_a, sum_b, pk);                            \
+        tmem_st_32x16(s_tmem + (CH) * 16, pk);                                 \
+        if (((CH) + 1) % (4 / ATT_P_SPLIT) == 0) {                             \
+            tmem_st_wait();                                                    \
+            tc_fence_before();                                                 \
+            __syncwarp();                                                      \
+            if (lane0) mbar_arrive(bar_pfull0 + 8u * ((CH) / (4 / ATT_P_SPLIT))); \
+        }                                                                      \
     }
-    SCAIL_ATT_P_CHUNK(sa, 0)
-    SCAIL_ATT_P_CHUNK(sb, 1)
+    SCAIL_ATT_P_CHUNK(s0, 0)
+    SCAIL_ATT_P_CHUNK(s1, 1)
+    SCAIL_ATT_P_CHUNK(s2, 2)
+    SCAIL_ATT_P_CHUNK(s3, 3)
 #undef SCAIL_ATT_P_CHUNK
     float la, lb, lc, ld;
     unpack_f32x2(sum_a, la, lb);
     unpack_f32x2(sum_b, lc, ld);
     l_run += (la + lb) + (lc + ld);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_pfull);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -161,15 +184,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t bar_base = v_smem + ATT_V_STAGES * ATT_TILE_BYTES;
     enum {
         B_QFULL = 0,
-        B_KFULL = 1,                       // [ATT_K_STAGES]
-        B_KEMPTY = B_KFULL + ATT_K_STAGES, // [ATT_K_STAGES]
-        B_VFULL = B_KEMPTY + ATT_K_STAGES, // [ATT_V_STAGES]
-        B_VEMPTY = B_VFULL + ATT_V_STAGES, // [ATT_V_STAGES]
-        B_SFULL = B_VEMPTY + ATT_V_STAGES, // [tile * 2 + half]
-        B_PFULL = B_SFULL + 4,             // [tile * 2 + half]
-        B_OFULL = B_PFULL + 4,             // [tile]
-        B_ODONE = B_OFULL + 2,             // [tile]: one phase per PV substep
-        B_COUNT = B_ODONE + 2
+        B_KFULL = 1,                        // [ATT_K_STAGES]
+        B_KEMPTY = B_KFULL + ATT_K_STAGES,  // [ATT_K_STAGES]
+        B_VFULL = B_KEMPTY + ATT_K_STAGES,  // [ATT_V_STAGES]
+        B_VEMPTY = B_VFULL + ATT_V_STAGES,  // [ATT_V_STAGES]
+        B_SFULL = B_VEMPTY + ATT_V_STAGES,  // [tile]
+        B_OFULL = B_SFULL + 2,              // [tile]
+        B_PFULL = B_OFULL + 2,              // [tile * ATT_P_SPLIT + group]
+        B_COUNT = B_PFULL + 2 * ATT_P_SPLIT
     };
     static_assert(8 * B_COUNT + 8 <= 256, "attention: barrier area");
     auto bar = [&](int i) { return bar_base + 8u * i; };
@@ -195,14 +217,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_init(bar(B_VFULL + s), 1);
             mbar_init(bar(B_VEMPTY + s), 1);
         }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bar(B_SFULL + i), 1);
-            mbar_init(bar(B_PFULL + i), 4);  // one arrive per softmax warp
-        }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(B_SFULL + i), 1);
             mbar_init(bar(B_OFULL + i), 1);
-            mbar_init(bar(B_ODONE + i), 1);
         }
+        for (int i = 0; i < 2 * ATT_P_SPLIT; ++i) mbar_init(bar(B_PFULL + i), 4);  // one arrive per softmax warp
         fence_barrier_init();
     }
     if (warp == 9) {
@@ -226,10 +245,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tma_load_2d(q_smem + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_q, bar(B_QFULL), col + h * 64,
                                 qrow + t * ATT_BQ);
             const int kvrow = batch * p.kv_batch_rows;
-            const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV;  // K/V tiles (TMA granularity)
+            const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV;
             auto load_k = [&](int j) {
                 const int s = j % ATT_K_STAGES;
                 mbar_wait(bar(B_KEMPTY + s), ((j / ATT_K_STAGES) & 1) ^ 1, 10);
+#ifdef SCAIL_ATTN_EXPERIMENTS
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) p.trace[j * 8 + 7] = clock64();
+#endif
                 mbar_expect_tx(bar(B_KFULL + s), ATT_TILE_BYTES);
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d(k_smem + s * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_k, bar(B_KFULL + s), col + h * 64,
@@ -252,22 +274,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
+        // The whole warp runs the control flow (waits, descriptor arithmetic stay warp-uniform => uniform
+        // datapath); only the tcgen05 instructions themselves are issued by the elected lane.
         const bool leader = elect_one_sync();
-        const int n_sub = (p.kv_len + ATT_SUB - 1) / ATT_SUB;  // 64-key substeps (pipeline granularity)
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_SUB, 0, 0);
+        const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV;
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
         const uint64_t q_desc0 = umma_desc_kmajor_sw128(q_smem), q_desc1 = umma_desc_kmajor_sw128(q_smem + ATT_TILE_BYTES);
         const uint64_t k_desc0 = umma_desc_kmajor_sw128(k_smem);
         const uint64_t v_desc0 = umma_desc_mnmajor_sw128(v_smem, ATT_HALF_BYTES);
-        constexpr uint64_t STAGE_STEP = ATT_TILE_BYTES >> 4;       // descriptor address units are 16 B
-        constexpr uint64_t K_HALF_STEP = (ATT_SUB * 128) >> 4;     // 64 key rows x 128 B inside each 64-column half
-        constexpr uint64_t V_KSTEP = 2048 >> 4;                    // 16 kv rows x 128 B
-        auto issue_qk = [&](int tile, int ks, int h) {
+        constexpr uint64_t STAGE_STEP = ATT_TILE_BYTES >> 4;  // descriptor address units are 16 B
+        constexpr int KSTEPS_PER_GROUP = 8 / ATT_P_SPLIT;     // 16-key UMMA k-steps fed by one P hand-over group
+        auto issue_qk = [&](int tile, int ks) {
 #ifdef SCAIL_ATTN_EXPERIMENTS
             if (p.debug == 5) return;
 #endif
-            const uint32_t d = tmem_base + tile * 128 + h * ATT_SUB;
-            const uint64_t qa = tile ? q_desc1 : q_desc0, kb = k_desc0 + ks * STAGE_STEP + h * K_HALF_STEP;
+            const uint32_t d = tmem_base + tile * 128;
+            const uint64_t qa = tile ? q_desc1 : q_desc0, kb = k_desc0 + ks * STAGE_STEP;
             if (leader) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -276,16 +299,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
             }
         };
-        auto issue_pv = [&](int tile, int vs, int h, bool acc) {
-#ifdef SCAIL_ATTN_EXPERIMENTS
-            if (p.debug == 6) return;
-#endif
+        // PV of one tile: group g's k-steps are issued as soon as the softmax warpgroup has handed that group of P over
+        auto issue_pv = [&](int tile, int vs, uint32_t parity, bool acc) {
             const uint32_t d = tmem_base + 256 + tile * 128;
-            const uint32_t a = tmem_base + tile * 128 + h * ATT_SUB;  // P aliases the first 32 columns of its S half
-            const uint64_t vb = v_desc0 + vs * STAGE_STEP + (h * 4) * V_KSTEP;
-            if (leader) {
+            const uint32_t a = tmem_base + tile * 128;  // P aliases S columns [0,64)
+            const uint64_t vb = v_desc0 + vs * STAGE_STEP;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ts(d, a + k * 8, vb + k * V_KSTEP, idesc_pv, acc || k != 0);
+            for (int g = 0; g < ATT_P_SPLIT; ++g) {
+                mbar_wait(bar(B_PFULL + tile * ATT_P_SPLIT + g), parity, 23 + tile);
+                tc_fence_after();
+#ifdef SCAIL_ATTN_EXPERIMENTS
+                if (p.debug == 6) continue;
+#endif
+                if (leader) {
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS_PER_GROUP; ++kk) {
+                        const int k = g * KSTEPS_PER_GROUP + kk;
+                        // 16 kv rows per step = 2048 B inside each 64-column half; halves are 16 KB apart (LBO)
+                        umma_ts(d, a + k * 8, vb + k * (2048 >> 4), idesc_pv, acc || k != 0);
+                    }
+                }
             }
         };
         auto commit = [&](int b) {
@@ -294,42 +327,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(bar(B_QFULL), 0, 20);
         mbar_wait(bar(B_KFULL + 0), 0, 21);
         tc_fence_after();
-        for (int h = 0; h < 2 && h < n_sub; ++h) {
-            issue_qk(0, 0, h);
-            commit(B_SFULL + h);
-            issue_qk(1, 0, h);
-            commit(B_SFULL + 2 + h);
-        }
+        issue_qk(0, 0);
+        commit(B_SFULL + 0);
+        issue_qk(1, 0);
+        commit(B_SFULL + 1);
         commit(B_KEMPTY + 0);
-        for (int s = 0; s < n_sub; ++s) {
-            const int j = s >> 1, h = s & 1;
+        for (int j = 0; j < n_kv; ++j) {
             const int vs = j % ATT_V_STAGES;
-            const bool more = s + 2 < n_sub;                 // substep s + 2 = (tile j + 1, same half)
+            const bool more = j + 1 < n_kv;
             const int ks = (j + 1) % ATT_K_STAGES;
-            const bool last = s == n_sub - 1;
-            if (h == 0) mbar_wait(bar(B_VFULL + vs), (j / ATT_V_STAGES) & 1, 22);
-            SCAIL_ATTN_TRACE_DECL_MMA
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                SCAIL_ATTN_TRACE(s * 8 + t * 2);
-                mbar_wait(bar(B_PFULL + t * 2 + h), j & 1, 23 + t);
-                SCAIL_ATTN_TRACE(s * 8 + t * 2 + 1);
+            mbar_wait(bar(B_VFULL + vs), (j / ATT_V_STAGES) & 1, 22);
+#ifdef SCAIL_ATTN_EXPERIMENTS
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && leader;
+#endif
+            SCAIL_ATTN_TRACE(j * 8 + 0);
+            issue_pv(0, vs, j & 1, j > 0);
+            SCAIL_ATTN_TRACE(j * 8 + 1);
+            if (more) {
+                mbar_wait(bar(B_KFULL + ks), ((j + 1) / ATT_K_STAGES) & 1, 24);
                 tc_fence_after();
-                issue_pv(t, vs, h, s > 0);
-                commit(B_ODONE + t);
-                if (more) {
-                    if (t == 0 && h == 0) {
-                        mbar_wait(bar(B_KFULL + ks), ((j + 1) / ATT_K_STAGES) & 1, 25);
-                        tc_fence_after();
-                    }
-                    issue_qk(t, ks, h);
-                    commit(B_SFULL + t * 2 + h);
-                } else if (last) {
-                    commit(B_OFULL + t);
-                }
+                issue_qk(0, ks);
+                commit(B_SFULL + 0);
+            } else {
+                commit(B_OFULL + 0);
             }
-            if (h == 1 || last) commit(B_VEMPTY + vs);                       // V tile j fully consumed
-            if (more && (h == 1 || s + 2 == n_sub - 1)) commit(B_KEMPTY + ks);  // K tile j + 1 fully consumed
+            SCAIL_ATTN_TRACE(j * 8 + 2);
+            issue_pv(1, vs, j & 1, j > 0);
+            SCAIL_ATTN_TRACE(j * 8 + 3);
+            commit(B_VEMPTY + vs);
+            if (more) {
+                issue_qk(1, ks);
+                commit(B_SFULL + 1);
+                commit(B_KEMPTY + ks);
+            } else {
+                commit(B_OFULL + 1);
+            }
         }
     } else if (warp < 8) {
         // ===================== softmax warpgroups (+ O rescale + epilogue) =====================
@@ -339,36 +371,35 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
         const uint32_t s_tmem = tmem_base + lane_off + tile * 128;
         const uint32_t o_tmem = tmem_base + lane_off + 256 + tile * 128;
+        const uint32_t bar_p0 = bar(B_PFULL + tile * ATT_P_SPLIT);
         float m_run = -INFINITY;  // running max, already multiplied by scale_log2
         float l_run = 0.f;
-        const int n_full = p.kv_len / ATT_SUB;  // unmasked substeps; an optional partial one follows (peeled)
-        for (int s = 0; s < n_full; ++s) {
-            const int h = s & 1;
+        const int n_full = p.kv_len / ATT_BKV;  // full tiles; an optional partial tile follows (peeled: no per-iteration branch)
+        for (int j = 0; j < n_full; ++j) {
 #ifdef SCAIL_ATTN_EXPERIMENTS
-            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < 64 && warp == 0 && lane == 0;
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
 #endif
-            SCAIL_ATTN_TRACE(s * 8 + 4);
-            mbar_wait(bar(B_SFULL + tile * 2 + h), (s >> 1) & 1, 30 + tile);
-            SCAIL_ATTN_TRACE(s * 8 + 5);
+            SCAIL_ATTN_TRACE(j * 8 + 4);
+            mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
+            SCAIL_ATTN_TRACE(j * 8 + 5);
             tc_fence_after();
 #ifdef SCAIL_ATTN_EXPERIMENTS
             if (p.debug == 1 || p.debug >= 5) {  // pipeline only: no TMEM reads, no math
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(B_PFULL + tile * 2 + h));
+                if (lane == 0)
+                    for (int g = 0; g < ATT_P_SPLIT; ++g) mbar_arrive(bar_p0 + 8u * g);
                 l_run = 1.f;
                 continue;
             }
 #endif
-            softmax_half<false>(s_tmem + h * ATT_SUB, o_tmem, p.scale_log2, ATT_SUB, s, m_run, l_run,
-                                bar(B_PFULL + tile * 2 + h), bar(B_ODONE + tile));
+            softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, ATT_BKV, j, m_run, l_run, bar_p0);
+            SCAIL_ATTN_TRACE(j * 8 + 6);
         }
-        if (n_full * ATT_SUB < p.kv_len) {  // partial last substep: masked instantiation
-            const int h = n_full & 1;
-            mbar_wait(bar(B_SFULL + tile * 2 + h), (n_full >> 1) & 1, 32 + tile);
+        if (n_full * ATT_BKV < p.kv_len) {  // partial last KV tile: masked instantiation
+            mbar_wait(bar(B_SFULL + tile), n_full & 1, 32 + tile);
             tc_fence_after();
-            softmax_half<true>(s_tmem + h * ATT_SUB, o_tmem, p.scale_log2, p.kv_len - n_full * ATT_SUB, n_full, m_run, l_run,
-                               bar(B_PFULL + tile * 2 + h), bar(B_ODONE + tile));
+            softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, p.kv_len - n_full * ATT_BKV, n_full, m_run, l_run, bar_p0);
         }
         // ---- epilogue: O / l -> bf16 -> global ----
         mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);

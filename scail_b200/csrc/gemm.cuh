@@ -3,7 +3,11 @@
 //   * one elected thread issues tcgen05.mma (UMMA 128x256x16, fp32 accumulators in TMEM),
 //   * TMEM accumulators are double-buffered (2 x 256 columns) so the epilogue of tile i
 //     overlaps the main loop of tile i+1,
-//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply the fused epilogue and store bf16.
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b: thread = row), apply bias / activation / gate in registers, then
+//     transpose 32x32 fp32 chunks through a swizzled shared-memory staging tile so that the residual read and the bf16
+//     store are row-contiguous (8 rows x 64 B per warp instruction instead of 32 rows x 16 B: every 32-byte sector is
+//     touched once and completely; the per-thread-row accesses of round 1 made the out-projection epilogue as long as its
+//     mainloop).
 // Replaces the reference's F.linear calls (sat/mpu/layers.py:230-243, :425-444) together with
 // the elementwise ops that follow them (bias, GELU-tanh, gate*out + residual).
 #pragma once
@@ -40,7 +44,8 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;  // one 32x32 fp32 chunk per epilogue warp
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 4 * GEMM_EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
 
 __device__ __forceinline__ void gemm_tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
@@ -65,7 +70,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;
+    const uint32_t epi_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;
+    const uint32_t bar_base = epi_base + 4 * GEMM_EPI_STAGE_BYTES;
     // barrier layout (8 B each): full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_STAGES + s); };
@@ -167,10 +173,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             gemm_tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + sub * 32 + lane;
-            const bool row_ok = row < p.M;
-            const int bidx = row_ok ? row / p.rows_per_batch : 0;
+            const int row = m_blk * GEMM_BM + sub * 32 + lane;  // phase 1: this thread's accumulator row
+            const int bidx = row < p.M ? row / p.rows_per_batch : 0;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * GEMM_BN;
+            const uint32_t stage = epi_base + sub * GEMM_EPI_STAGE_BYTES;
+            // phase 2 mapping: 4 lanes per row (8 columns each), 8 rows per instruction
+            const int r2 = lane >> 2, cg = lane & 3;
 #pragma unroll 1
             for (int c = 0; c < GEMM_BN / 32; ++c) {
                 const int col0 = n_blk * GEMM_BN + c * 32;
@@ -178,64 +186,83 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
                 tmem_ld_wait();
-                if (row_ok) {
+                // ---- phase 1 (thread = row): bias, activation, gate in fp32; park the chunk in the staging tile ----
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // groups of 8 columns (16 B of bf16)
-                        const int col = col0 + g * 8;
-                        if (col < p.N) {
-                            float f[8];
+                for (int g = 0; g < 4; ++g) {  // groups of 8 columns
+                    const int col = col0 + g * 8;
+                    float f[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                            if (p.bias) {
-                                uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
-                                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                    if (col < p.N) {
+                        if (p.bias) {
+                            uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);  // warp-uniform address: broadcast
+                            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 b2 = unpack_bf16(bw[j]);
-                                    f[2 * j] += b2.x;
-                                    f[2 * j + 1] += b2.y;
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                float2 b2 = unpack_bf16(bw[j]);
+                                f[2 * j] += b2.x;
+                                f[2 * j + 1] += b2.y;
                             }
-                            if (p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_SILU ||
-                                p.epilogue == EPI_BIAS_GELU_ERF) {
+                        }
+                        if (p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_SILU || p.epilogue == EPI_BIAS_GELU_ERF) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = epi_act(f[j], p.epilogue);
-                            }
-                            if (p.epilogue == EPI_BIAS_GATE_RES) {
-                                uint4 gv = *reinterpret_cast<const uint4*>(p.gate + bidx * p.gate_stride + col);
-                                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                            for (int j = 0; j < 8; ++j) f[j] = epi_act(f[j], p.epilogue);
+                        }
+                        if (p.epilogue == EPI_BIAS_GATE_RES) {
+                            uint4 gv = *reinterpret_cast<const uint4*>(p.gate + bidx * p.gate_stride + col);
+                            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 g2 = unpack_bf16(gw[j]);
-                                    f[2 * j] *= g2.x;
-                                    f[2 * j + 1] *= g2.y;
-                                }
-                            }
-                            if (p.epilogue == EPI_BIAS_GATE_RES || p.epilogue == EPI_BIAS_RES) {
-                                uint4 rv = *reinterpret_cast<const uint4*>(p.residual + static_cast<int64_t>(row) * p.ldr + col);
-                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 r2 = unpack_bf16(rw[j]);
-                                    f[2 * j] += r2.x;
-                                    f[2 * j + 1] += r2.y;
-                                }
-                            }
-                            if (p.C32) {
-                                float4* o = reinterpret_cast<float4*>(p.C32 + static_cast<int64_t>(row) * p.ldc + col);
-                                o[0] = make_float4(f[0], f[1], f[2], f[3]);
-                                o[1] = make_float4(f[4], f[5], f[6], f[7]);
-                            } else {
-                                uint4 o;
-                                o.x = pack_bf16(f[0], f[1]);
-                                o.y = pack_bf16(f[2], f[3]);
-                                o.z = pack_bf16(f[4], f[5]);
-                                o.w = pack_bf16(f[6], f[7]);
-                                *reinterpret_cast<uint4*>(p.C + static_cast<int64_t>(row) * p.ldc + col) = o;
+                            for (int j = 0; j < 4; ++j) {
+                                float2 g2 = unpack_bf16(gw[j]);
+                                f[2 * j] *= g2.x;
+                                f[2 * j + 1] *= g2.y;
                             }
                         }
                     }
+                    // row `lane` = 128 B = 8 chunks of 16 B; chunk q lives at position q ^ (lane & 7): conflict-free both ways
+                    const uint32_t a0 = stage + lane * 128 + (((2 * g) ^ (lane & 7)) << 4);
+                    const uint32_t a1 = stage + lane * 128 + (((2 * g + 1) ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
                 }
+                __syncwarp();
+                // ---- phase 2 (4 lanes per row): residual add, one bf16 rounding, row-contiguous stores ----
+                const int col = col0 + cg * 8;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + r2;
+                    const int grow = m_blk * GEMM_BM + sub * 32 + rr;
+                    float f[8];
+                    const uint32_t a0 = stage + rr * 128 + (((2 * cg) ^ (rr & 7)) << 4);
+                    const uint32_t a1 = stage + rr * 128 + (((2 * cg + 1) ^ (rr & 7)) << 4);
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(a0) : "memory");
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "r"(a1) : "memory");
+                    if (grow < p.M && col < p.N) {
+                        if (p.epilogue == EPI_BIAS_GATE_RES || p.epilogue == EPI_BIAS_RES) {
+                            uint4 rv = *reinterpret_cast<const uint4*>(p.residual + static_cast<int64_t>(grow) * p.ldr + col);
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 r2f = unpack_bf16(rw[j]);
+                                f[2 * j] += r2f.x;
+                                f[2 * j + 1] += r2f.y;
+                            }
+                        }
+                        if (p.C32) {
+                            float4* o = reinterpret_cast<float4*>(p.C32 + static_cast<int64_t>(grow) * p.ldc + col);
+                            o[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            o[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        } else {
+                            uint4 o;
+                            o.x = pack_bf16(f[0], f[1]);
+                            o.y = pack_bf16(f[2], f[3]);
+                            o.z = pack_bf16(f[4], f[5]);
+                            o.w = pack_bf16(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(p.C + static_cast<int64_t>(grow) * p.ldc + col) = o;
+                        }
+                    }
+                }
+                __syncwarp();  // the staging tile is rewritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();

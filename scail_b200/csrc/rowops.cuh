@@ -5,12 +5,27 @@
 
 namespace scail {
 
-constexpr int ROW_MAXV = 20;  // up to 20 uint4 (=160 bf16) per lane -> D <= 5120, D % 256 == 0
+// Row kernels: ONE 128-thread block per row, each thread holds <= ROW_MAXV 16-byte vectors (D <= 5120, D % 8 == 0).
+// Round 1 used a warp per row (20 vectors = 80+ data registers per lane -> 194 registers, one 8-warp block per SM whose
+// warps load, reduce and store in lockstep, so reads and writes never overlapped: 0.44-0.46 of HBM peak).  With ~48
+// registers per thread, 16 rows are resident per SM at independent phases, which is what keeps HBM busy in both directions.
+constexpr int ROW_THREADS = 128;
+constexpr int ROW_MAXV = 5;  // vectors per thread: 5 * 128 * 8 = 5120 columns
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// sum over the 128-thread block; `red` is a 4-float shared scratch (one slot per warp), safe to reuse after the call returns
+__device__ __forceinline__ float row_block_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float t = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    return t;
 }
 
 struct LnModParams {
@@ -31,21 +46,21 @@ struct LnModParams {
 
 // LayerNorm (+optional affine) (+optional AdaLN modulate x*(1+scale)+shift).
 // Restates F.layer_norm + modulate (dit_video_crossattn_sc_xc.py:760-761, :1031-1032, :1045-1046, :825).
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= p.total_rows) return;
-    const int b = warp / p.rows_out;
-    const int r = warp - b * p.rows_out;
+__global__ void __launch_bounds__(ROW_THREADS) ln_modulate_kernel(const LnModParams p) {
+    __shared__ float red[4];
+    const int row = blockIdx.x;
+    const int b = row / p.rows_out;
+    const int r = row - b * p.rows_out;
     const int64_t in_row = static_cast<int64_t>(b) * p.in_batch_rows + p.in_row_offset + r;
     const uint4* xin = reinterpret_cast<const uint4*>(p.x + in_row * p.D);
-    const int nvec = p.D >> 8;  // vectors per lane
+    const int nvec = p.D >> 3;  // 16-byte vectors in the row
     uint4 v[ROW_MAXV];
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
-        if (j < nvec) {
-            v[j] = xin[j * 32 + lane];
+        const int i = j * ROW_THREADS + threadIdx.x;
+        if (i < nvec) {
+            v[j] = xin[i];
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -54,11 +69,11 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
             }
         }
     }
-    const float mean = warp_sum(sum) / p.D;
+    const float mean = row_block_sum(sum, red) / p.D;
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
-        if (j < nvec) {
+        if (j * ROW_THREADS + threadIdx.x < nvec) {
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -67,12 +82,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / p.D + p.eps);
-    uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(warp) * p.D);
+    const float rstd = rsqrtf(row_block_sum(sq, red) / p.D + p.eps);
+    uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.D);
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
-        if (j < nvec) {
-            const int col = (j * 32 + lane) * 8;
+        const int i = j * ROW_THREADS + threadIdx.x;
+        if (i < nvec) {
+            const int col = i * 8;
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
             float f[8];
 #pragma unroll
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
             ov.y = pack_bf16(f[2], f[3]);
             ov.z = pack_bf16(f[4], f[5]);
             ov.w = pack_bf16(f[6], f[7]);
-            o[j * 32 + lane] = ov;
+            o[i] = ov;
         }
     }
 }
@@ -119,7 +135,7 @@ struct RmsRopeParams {
     int col_offset[2];    // column offset of slab 0 / slab 1 (e.g. q and k inside the fused QKV buffer)
     const __nv_bfloat16* weight[2];
     int nslabs;           // 1 or 2
-    int D;                // normalised width (hidden size), D % 256 == 0
+    int D;                // normalised width (hidden size), D % 8 == 0 (D % 128 == 0 with RoPE)
     int rows;             // total rows (B * rows_per_batch)
     int rows_per_batch;
     const float* cos;     // optional [rows_per_batch, 128] fp32 tables (token = row % rows_per_batch)
@@ -129,20 +145,20 @@ struct RmsRopeParams {
 
 // RMSNorm over the full hidden width (dit_video_crossattn_sc_xc.py:61-68, F5) fused with the
 // interleaved-pair 3-D RoPE (:336-340, :525-645).  grid.y selects the slab (q / k).
-__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsRopeParams p) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(ROW_THREADS) rmsnorm_rope_kernel(const RmsRopeParams p) {
+    __shared__ float red[4];
+    const int row = blockIdx.x;
     const int slab = blockIdx.y;
-    if (warp >= p.rows) return;
-    __nv_bfloat16* base = p.buf + static_cast<int64_t>(warp) * p.ld + p.col_offset[slab];
+    __nv_bfloat16* base = p.buf + static_cast<int64_t>(row) * p.ld + (slab ? p.col_offset[1] : p.col_offset[0]);
     uint4* xin = reinterpret_cast<uint4*>(base);
-    const int nvec = p.D >> 8;
+    const int nvec = p.D >> 3;
     uint4 v[ROW_MAXV];
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
-        if (j < nvec) {
-            v[j] = xin[j * 32 + lane];
+        const int i = j * ROW_THREADS + threadIdx.x;
+        if (i < nvec) {
+            v[j] = xin[i];
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -151,24 +167,24 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsRopeParams p
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / p.D + p.eps);
-    // head_dim = 128 = 16 vectors: the rope column (col % 128) of lane i is (i % 16) * 8 for every vector j
-    float cs[8], sn[8];
+    // head_dim = 128 = 16 vectors and ROW_THREADS % 16 == 0: the rope column (col % 128) of a thread is (tid % 16) * 8
+    // for every vector it owns, so one (cos, sin) octet per thread serves the whole row; fetched before the reduction
+    // so that its latency hides behind it
+    float4 ca, cb, sa, sb;
     const bool rope = p.cos != nullptr;
     if (rope) {
-        const int tok = warp % p.rows_per_batch;
-        const float4* c4 = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(tok) * 128 + (lane & 15) * 8);
-        const float4* s4 = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(tok) * 128 + (lane & 15) * 8);
-        float4 a = c4[0], bq = c4[1], c = s4[0], d = s4[1];
-        cs[0] = a.x; cs[1] = a.y; cs[2] = a.z; cs[3] = a.w; cs[4] = bq.x; cs[5] = bq.y; cs[6] = bq.z; cs[7] = bq.w;
-        sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w; sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
+        const int tok = row % p.rows_per_batch;
+        const float4* c4 = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(tok) * 128 + (threadIdx.x & 15) * 8);
+        const float4* s4 = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(tok) * 128 + (threadIdx.x & 15) * 8);
+        ca = c4[0]; cb = c4[1]; sa = s4[0]; sb = s4[1];
     }
-    const __nv_bfloat16* wgt = p.weight[slab];
+    const float rstd = rsqrtf(row_block_sum(sq, red) / p.D + p.eps);
+    const __nv_bfloat16* wgt = slab ? p.weight[1] : p.weight[0];  // (a dynamic index would spill the param arrays to local memory)
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
-        if (j < nvec) {
-            const int col = (j * 32 + lane) * 8;
-            uint4 g = *reinterpret_cast<const uint4*>(wgt + col);
+        const int i = j * ROW_THREADS + threadIdx.x;
+        if (i < nvec) {
+            uint4 g = *reinterpret_cast<const uint4*>(wgt + i * 8);
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, gw[4] = {g.x, g.y, g.z, g.w};
             float f[8];
 #pragma unroll
@@ -178,6 +194,8 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsRopeParams p
                 f[2 * k + 1] = g2.y * (t.y * rstd);
             }
             if (rope) {
+                const float cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                const float sn[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float x1 = f[2 * k], x2 = f[2 * k + 1];
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(const RmsRopeParams p
             ov.y = pack_bf16(f[2], f[3]);
             ov.z = pack_bf16(f[4], f[5]);
             ov.w = pack_bf16(f[6], f[7]);
-            xin[j * 32 + lane] = ov;
+            xin[i] = ov;
         }
     }
 }

@@ -52,13 +52,32 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
         "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(cta_rank) : "memory");
 }
+// SCAIL_MBAR_MODE: 0 = try_wait with a long suspend-time hint (the warp sleeps in hardware until the phase completes),
+// 1 = plain try_wait (implementation-default suspend window; what CUTLASS' ClusterBarrier::wait spins on), 2 = test_wait (pure spin).
+#ifndef SCAIL_MBAR_MODE
+#define SCAIL_MBAR_MODE 1
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
+#if SCAIL_MBAR_MODE == 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");  // suspend-time hint: sleep in HW, not spin
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+#elif SCAIL_MBAR_MODE == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
     return done != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) after ~4 s instead of a hung GPU.

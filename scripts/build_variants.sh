@@ -1,12 +1,17 @@
 #!/bin/bash
-# Build attention A/B variants of the library (scripts/perf_attn_variants.py picks them with SCAIL_LIB_VARIANT).
+# Build attention A/B variants of the library (scripts/perf_attn.py / trace_attn.py pick them with SCAIL_LIB_VARIANT).
 cd "$(dirname "$0")/.."
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"
 build() { nvcc $F $2 -o scail_b200/libscail_b200_$1.so scail_b200/csrc/api.cu -lcudart & }
-build p0k3  "-DSCAIL_ATT_POLY_MASK=0x0u"
-build p25k3 "-DSCAIL_ATT_POLY_MASK=0x8888u"
-build p37k3 "-DSCAIL_ATT_POLY_MASK=0x9249u"
-build p50k3 "-DSCAIL_ATT_POLY_MASK=0xAAAAu"
-build p25k2 "-DSCAIL_ATT_POLY_MASK=0x8888u -DSCAIL_ATT_K_STAGES=2"
+rm -f scail_b200/libscail_b200_*.so
+build s1p0  "-DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x0u"
+build s4p0  "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x0u"
+build s1p25 "-DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x8888u"
+build s2p25 "-DSCAIL_ATT_P_SPLIT=2 -DSCAIL_ATT_POLY_MASK=0x8888u"
+build s4p25 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x8888u"
+build s4p37 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x9249u"
+build s4p50 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0xAAAAu"
+build x4p25 "-DSCAIL_ATTN_EXPERIMENTS -DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x8888u"
+build x1p0 "-DSCAIL_ATTN_EXPERIMENTS -DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x0u"
 wait
-ls -la scail_b200/*.so
+ls scail_b200/*.so

@@ -12,8 +12,15 @@ using namespace scail;
 
 struct Case { int ts; int n; int m256; const char* name; };
 
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// TS: 0 = A,B from smem (K-major); 1 = A from TMEM, B K-major; 2 = A from TMEM, B MN-major (attention's P V)
+// filler > 0: LSU st.shared traffic; filler < 0: a TMA warp streams -filler KB per 32 MMAs from global (L2) into a smem ring
 template <int TS, int N>
-__global__ void __launch_bounds__(256, 1) bench(long long* out, int iters, int filler) {
+__global__ void __launch_bounds__(256, 1) bench(long long* out, int iters, int filler, const uint8_t* gsrc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_smem = base;               // 128 x 128 bf16 (two 64-col halves, 32 KB)
@@ -33,7 +40,9 @@ __global__ void __launch_bounds__(256, 1) bench(long long* out, int iters, int f
     if (warp == 0) {
         const bool leader = elect_one_sync();
         constexpr uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
-        const uint64_t ad = umma_desc_kmajor_sw128(a_smem), bd = umma_desc_kmajor_sw128(b_smem);
+        const uint64_t ad = umma_desc_kmajor_sw128(a_smem);
+        const uint64_t bd = TS == 2 ? umma_desc_mnmajor_sw128(b_smem, 16384) : umma_desc_kmajor_sw128(b_smem);
+        constexpr uint32_t idesc_mn = umma_idesc_bf16(128, N, 0, 1);
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
             if (leader) {
@@ -41,7 +50,8 @@ __global__ void __launch_bounds__(256, 1) bench(long long* out, int iters, int f
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
                     const uint64_t boff = ((k >> 2) * (N * 128) + (k & 3) * 32) >> 4;
-                    if (TS) umma_ts(tmem + 256, tmem + k * 8, bd + boff, idesc, 1);
+                    if (TS == 2) umma_ts(tmem + 256, tmem + k * 8, bd + k * (2048 >> 4), idesc_mn, 1);
+                    else if (TS) umma_ts(tmem + 256, tmem + k * 8, bd + boff, idesc, 1);
                     else umma_ss<1>(tmem + 256 * 0 + (it & 1) * 0, ad + off, bd + boff, idesc, 1);
                 }
             }
@@ -50,7 +60,27 @@ __global__ void __launch_bounds__(256, 1) bench(long long* out, int iters, int f
         mbar_wait(bar, 0);
         long long t1 = clock64();
         if (lane == 0) out[blockIdx.x] = t1 - t0;
-    } else if (filler && warp >= 4) {
+    } else if (filler < 0 && warp == 1) {
+        // TMA traffic: per 32 MMAs (= 4 iterations), -filler KB in 16 KB bulk copies into a 64 KB ring; completion tracked on a
+        // second mbarrier that this lane polls before reusing a slot (keeps at most 4 copies in flight)
+        if (lane == 0) {
+            const uint32_t ring = base + 32768 + 65536, tbar = bar + 8;
+            mbar_init(tbar, 1);
+            fence_barrier_init();
+            const int chunks = (-filler) / 16;
+            uint32_t phase = 0;
+            int slot_i = 0;
+            for (int it = 0; it < iters / 4; ++it) {
+                mbar_expect_tx(tbar, chunks * 16384);
+                for (int c = 0; c < chunks; ++c) {
+                    bulk_g2s(ring + (slot_i & 3) * 16384, gsrc + ((blockIdx.x * 7 + slot_i) & 63) * 16384, 16384, tbar);
+                    ++slot_i;
+                }
+                mbar_wait(tbar, phase);
+                phase ^= 1;
+            }
+        }
+    } else if (filler > 0 && warp >= 4) {
         // emulate TMA fill traffic: plain shared-memory stores into a scratch region at ~filler bytes per 64 cycles
         const uint32_t scratch = base + 32768 + 65536;
         const int tid = threadIdx.x - 128;
@@ -69,13 +99,15 @@ void run(const char* name, int filler) {
     const int iters = 2000, smem = 32768 + 65536 + 65536 + 1024 + 64;
     long long* d;
     cudaMalloc(&d, 148 * sizeof(long long));
+    static uint8_t* gsrc = nullptr;
+    if (!gsrc) { cudaMalloc(&gsrc, 64 * 16384); cudaMemset(gsrc, 0x3c, 64 * 16384); }
     cudaFuncSetAttribute(bench<TS, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    bench<TS, N><<<148, 256, smem>>>(d, 100, filler);
+    bench<TS, N><<<148, 256, smem>>>(d, 100, filler, gsrc);
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    bench<TS, N><<<148, 256, smem>>>(d, iters, filler);
+    bench<TS, N><<<148, 256, smem>>>(d, iters, filler, gsrc);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms = 0;
@@ -100,8 +132,15 @@ int main() {
     run<1, 64>("TS 128x64x16", 0);
     run<1, 128>("TS 128x128x16", 0);
     run<1, 256>("TS 128x256x16", 0);
-    run<0, 128>("SS 128x128x16", 4);
-    run<1, 128>("TS 128x128x16", 4);
-    run<0, 256>("SS 128x256x16", 4);
+    run<2, 128>("TS-MNmajorB 128x128x16", 0);
+    run<0, 128>("SS 128x128x16 + TMA 32KB/32mma", -32);
+    run<0, 128>("SS 128x128x16 + TMA 64KB/32mma", -64);
+    run<0, 128>("SS 128x128x16 + TMA 128KB/32mma", -128);
+    run<1, 128>("TS 128x128x16 + TMA 64KB/32mma", -64);
+    run<2, 128>("TS-MNmajorB 128x128x16 + TMA 64KB/32mma", -64);
+    run<0, 256>("SS 128x256x16 + TMA 48KB/32mma", -48);
+    run<0, 256>("SS 128x256x16 + TMA 96KB/32mma", -96);
+    run<0, 256>("SS 128x256x16 + TMA 384KB/32mma (GEMM ratio)", -384);
+    run<0, 128>("SS 128x128x16 + TMA 256KB/32mma", -256);
     return 0;
 }

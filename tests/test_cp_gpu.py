@@ -39,8 +39,23 @@ def _worker(rank, world, port, q):
             single = m(x, **kw).float()
             m.mixins["adaln_layer"].cp = ContextParallel()
             multi = m(x, **kw).float()
+            # ---- engine-style sequence parallelism (diffusion_video.py:495-552): every rank gets its H- (or W-) chunk of the
+            # latents / ref / pose, passes chunk_dim, and returns its chunk of the output; the engine gathers on chunk_dim ----
+            rels = []
+            for chunk_dim in (3, 4):
+                ck = lambda a: torch.chunk(a, world, dim=chunk_dim)[rank].contiguous()
+                kwc = dict(kw, ref_concat=ck(ref), concat_smpl_render=ck(pose), concat_images=ck(x), chunk_dim=chunk_dim)
+                loc = m(ck(x), **kwc).float()
+                want = torch.chunk(single, world, dim=chunk_dim)[rank]
+                rels.append(float((loc - want).norm() / want.norm()))
+                # the same through the SAT hook sequence (BaseTransformer.forward's calls), i.e. the drop-in mixin path
+                import sys
+                sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+                from sat_driver import drive_hooks
+                hk = drive_hooks(m, ck(x), ts, ctx, ck(ref), ck(pose), clip, chunk_dim=chunk_dim, sp_rank=rank).float()
+                rels.append(float((hk - want).norm() / want.norm()))
         torch.cuda.synchronize()
-        rel = float((multi - single).norm() / single.norm())
+        rel = max([float((multi - single).norm() / single.norm())] + rels)
         q.put((rank, rel))
         dist.destroy_process_group()
     except Exception as e:  # pragma: no cover
