@@ -210,7 +210,7 @@ def run_reference_arm(args):
     print(json.dumps({"impl": "reference", "metric": "denoising steps/sec (SCAIL-14B, 512p/81f)", "value": v,
                       "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                      "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+                      "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus, parallelism_name(args.gpus, args.parallel)),
                       "cpu_baseline": cb, "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0,
                                                   "d2h_bytes_per_step": 0}}))
 
@@ -288,13 +288,13 @@ def vae_decode_bench(dev, peaks):
     return out
 
 
-def cp_consistency_check(model, d, cond, uc, sig, rank, dist, layers=2):
+def cp_consistency_check(model, d, cond, uc, sig, rank, dist, plan=None, layers=2):
     """N > 1: the first `layers` blocks of step 0 computed (a) context-parallel over all ranks and (b) on rank 0 alone with
     the single-GPU path; returns relL2 of (a) vs (b) on rank 0 (None elsewhere) so the scaling run carries correctness."""
     from scail_b200 import sampler
     ad = model.mixins["adaln_layer"]
     x0 = d["x"].clone()
-    a = sampler.sampler_step(model, x0.clone(), sig[0], sig[1], cond, uc, 4.0, _num_layers=layers)
+    a = sampler.sampler_step(model, x0.clone(), sig[0], sig[1], cond, uc, 4.0, plan=plan, _num_layers=layers)
     rel = None
     if rank == 0:
         cp, ad.cp = ad.cp, None
@@ -309,11 +309,21 @@ def cp_consistency_check(model, d, cond, uc, sig, rank, dist, layers=2):
     return rel
 
 
-def workload_config(n_gpus):
+def parallelism_name(n_gpus, mode="auto"):
+    if n_gpus <= 1:
+        return "single"
+    if mode == "auto":
+        mode = "cfgxcp" if n_gpus % 2 == 0 else "cp"
+    if mode == "cfgxcp":
+        return f"cfg2xcp{n_gpus // 2}" if n_gpus > 2 else "cfg2"
+    return f"cp{n_gpus}"
+
+
+def workload_config(n_gpus, parallelism=None):
     return {"workload": f"SCAIL-14B one sampler step (CFG batch-2 DiT forward + CFG + Euler), latent {T_LAT}x{H_LAT}x{W_LAT} "
                         f"({8 * H_LAT}x{8 * W_LAT}, {4 * (T_LAT - 1) + 1} frames), N={seq_len()} tokens (ref | noise | pose), 40 blocks, "
                         "d=5120, 40 heads x 128, MLP 13824, text 512 + CLIP 257 keys",
-            "global_batch": 2, "seq_len": seq_len(), "parallelism": f"cp{n_gpus}" if n_gpus > 1 else "single",
+            "global_batch": 2, "seq_len": seq_len(), "parallelism": parallelism or parallelism_name(n_gpus),
             "l2_policy": "inputs larger than L2 (32 GB weights, >5 GB activations per step)"}
 
 
@@ -323,6 +333,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torchlib"])
+    ap.add_argument("--parallel", default="auto", choices=["auto", "cp", "cfgxcp"],
+                    help="N > 1 layout: cp = tokens sharded over all ranks (one K/V all-gather per block); cfgxcp = the two CFG "
+                         "branches on the two halves of the ranks, context parallel inside each half (default when N is even)")
     ap.add_argument("--no-extras", action="store_true", help="skip library_baseline / kernel_compare / vae_decode (profiling runs)")
     ap.add_argument("--layers", type=int, default=LAYERS, help=argparse.SUPPRESS)  # debugging only; default = full model
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
@@ -346,9 +359,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(dev, layers=args.layers)
+    plan = None
+    par = "single"
     if world > 1:
-        from scail_b200.parallel import ContextParallel
-        model.mixins["adaln_layer"].cp = ContextParallel(dist.group.WORLD)
+        from scail_b200.parallel import ContextParallel, HybridParallel
+        mode = args.parallel if args.parallel != "auto" else ("cfgxcp" if world % 2 == 0 else "cp")
+        if mode == "cfgxcp":
+            plan = HybridParallel()
+            model.mixins["adaln_layer"].cp = plan.cp
+            par = f"cfg2xcp{plan.cp_size}" if plan.cp_size > 1 else "cfg2"
+        else:
+            model.mixins["adaln_layer"].cp = ContextParallel(dist.group.WORLD)
+            par = f"cp{world}"
     host = synthetic_inputs()
     d = {k: v.to(dev) for k, v in host.items()}
     cond = dict(crossattn=d["context_cond"], ref_concat=d["ref_concat"], concat_smpl_render=d["concat_smpl_render"],
@@ -372,12 +394,12 @@ def main():
         if lib_arm:
             x.copy_(torchlib.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0))
         else:
-            sampler.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0)
+            sampler.sampler_step(model, x, sig[j], sig[j + 1], cond, uc, 4.0, plan=plan)
 
     cp_check = None
     with torch.no_grad():
         if world > 1:
-            cp_check = cp_consistency_check(model, d, cond, uc, sig, rank, dist)
+            cp_check = cp_consistency_check(model, d, cond, uc, sig, rank, dist, plan)
         for i in range(args.warmup):
             step(i)
         # ---- timed region: device-resident inputs ----
@@ -398,7 +420,7 @@ def main():
         attn_ms = [a.elapsed_time(b) for a, b in ops.ATTN_EVENTS]
         ops.ATTN_EVENTS = None
         # ---- e2e: host buffers through the public API ----
-        hs = sampler.HostStep(model, host, dev, step_fn=torchlib.sampler_step if lib_arm else None)
+        hs = sampler.HostStep(model, host, dev, step_fn=torchlib.sampler_step if lib_arm else None, plan=plan)
         hs(sig[0], sig[1])
         barrier()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -427,7 +449,7 @@ def main():
     out = {"metric": "denoising steps/sec (SCAIL-14B, 512p/81f)", "value": value, "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init 14B weights, seeded N(0,1) inputs)",
-           "config": workload_config(world), "fwd_per_s": 2 * value,
+           "config": workload_config(world, par), "fwd_per_s": 2 * value,
            "step_tflops": step_flops / 1e12, "achieved_tflops_per_gpu": step_flops / world / ms / 1e9,
            "frac_of_bf16_sustained_peak": step_flops / world / ms / 1e9 / peaks["bf16_tflops_sustained"],
            "frac_of_bf16_burst_peak": step_flops / world / ms / 1e9 / peaks["bf16_tflops"],

@@ -160,20 +160,30 @@ int make_tmap_cl4d(const void* ptr, uint64_t T, uint64_t H, uint64_t W, uint64_t
 }
 
 long long* g_attn_trace = nullptr;  // perf experiments only
-int g_sm_count = 0;
+constexpr int MAX_DEVICES = 64;
+int g_sm_count[MAX_DEVICES] = {0};  // per device: a process may drive several GPUs
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_sm_count;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+    if (g_sm_count[dev] == 0) cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    return g_sm_count[dev];
 }
 
-std::unordered_map<const void*, cudaError_t> g_smem_done;  // keyed by kernel address (instantiations share a type)
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+struct SmemKey {
+    const void* fn; int dev;
+    bool operator==(const SmemKey& o) const { return fn == o.fn && dev == o.dev; }
+};
+struct SmemKeyHash {
+    size_t operator()(const SmemKey& k) const { return reinterpret_cast<size_t>(k.fn) * 31u + static_cast<size_t>(k.dev); }
+};
+std::unordered_map<SmemKey, cudaError_t, SmemKeyHash> g_smem_done;  // MaxDynamicSharedMemorySize is a per-device function attribute
 template <typename K>
 int set_smem(K kernel, int bytes) {
-    const void* key = reinterpret_cast<const void*>(kernel);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(-2, "no current CUDA device");
+    const SmemKey key{reinterpret_cast<const void*>(kernel), dev};
     cudaError_t err;
     {
         std::lock_guard<std::mutex> lk(g_map_mu);
@@ -242,7 +252,10 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     using namespace scail;
     SCAIL_REQUIRE(A && W && C, "gemm: null operand");
     SCAIL_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
-    SCAIL_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0, "gemm: N, K, lda, ldw must be multiples of 8");
+    SCAIL_REQUIRE(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % (c_fp32 ? 4 : 8) == 0,
+                  "gemm: N, K, lda, ldw (and ldc for a bf16 output; ldc %% 4 for fp32) must be multiples of 8");
+    SCAIL_REQUIRE(aligned16(C) && aligned16(bias) && aligned16(gate) && aligned16(residual),
+                  "gemm: C, bias, gate and residual must be 16-byte aligned (the epilogue uses 16-byte accesses)");
     SCAIL_REQUIRE(epilogue >= 0 && epilogue <= 5, "gemm: unknown epilogue %d", epilogue);
     if (epilogue == EPI_BIAS_GATE_RES) SCAIL_REQUIRE(gate && residual && gate_stride % 8 == 0, "gemm: gate/residual required");
     if (epilogue == EPI_BIAS_RES) SCAIL_REQUIRE(residual, "gemm: residual required");
@@ -320,6 +333,7 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
     SCAIL_REQUIRE(Q && K && V && out, "attention: null operand");
     SCAIL_REQUIRE(B > 0 && H > 0 && q_len > 0 && kv_len > 0, "attention: bad shape");
     SCAIL_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
+    SCAIL_REQUIRE(aligned16(out), "attention: out must be 16-byte aligned");
     SCAIL_REQUIRE(q_len <= q_batch_rows && kv_len <= kv_batch_rows && B * q_batch_rows <= q_rows_total + (q_batch_rows - q_len) &&
                       B * kv_batch_rows <= kv_rows_total + (kv_batch_rows - kv_len),
                   "attention: row extents inconsistent");
@@ -421,6 +435,7 @@ int scail_conv3d_cl(const void* x, int64_t T, int64_t H, int64_t W, int64_t Cin,
     SCAIL_REQUIRE(KT >= 1 && KT <= 3 && KH >= 1 && KH <= 3 && KW >= 1 && KW <= 3 && (KH & 1) && (KW & 1), "conv3d: taps must be 1 or 3");
     SCAIL_REQUIRE(epilogue >= 0 && epilogue <= 2, "conv3d: unknown epilogue");
     if (epilogue == CONV_EPI_BIAS_RES) SCAIL_REQUIRE(residual && ldr % 8 == 0, "conv3d: residual required");
+    SCAIL_REQUIRE(aligned16(out) && aligned16(bias) && aligned16(residual) && aligned16(out2), "conv3d: out, bias, residual must be 16-byte aligned");
     if (epilogue == CONV_EPI_HEAD_CLAMP) SCAIL_REQUIRE(bias && Cout <= 16, "conv3d: head epilogue needs bias and Cout <= 16");
     else SCAIL_REQUIRE(Cout % 8 == 0 && ldo % 8 == 0 && ocols > 0 && ocols % 8 == 0, "conv3d: Cout, ldo, ocols must be multiples of 8");
     const int taps = KT * KH * KW;

@@ -105,3 +105,33 @@ class ContextParallel:
         ops.attention(q, kv2[:, :d], kv2[:, d:], ctx, B, H, n_local, P * n_local, q_batch_rows=n_local,
                       kv_batch_rows=P * n_local)
         return ctx
+
+
+class HybridParallel:
+    """CFG-parallel x context-parallel layout.  The two classifier-free-guidance branches of a sampler
+    step are independent forwards (guiders.py:47-57 only concatenates them on the batch axis), so with an even world size
+    W = 2 * cp_size the ranks split into two halves: ranks [0, cp_size) run the UNCOND branch, ranks [cp_size, W) the COND
+    branch, each half with context parallelism over its own cp_size ranks (b = 1 per rank: every GEMM / attention launch has
+    twice the rows per rank of the pure-CP layout at the same W, and the K/V all-gather volume per rank halves).  The only
+    cross-half traffic is one all-gather of the branch velocity (5.5 MB at 512p/81f) per step between partner ranks
+    (i, i + cp_size), after which every rank applies the same CFG combine + Euler update to its replicated fp32 latent.
+    W = 2 is pure CFG parallelism (no K/V collective at all)."""
+
+    def __init__(self):
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world % 2:
+            raise ValueError(f"HybridParallel needs an even world size, got {world}")
+        self.world, self.rank = world, rank
+        self.cp_size = world // 2
+        self.branch = rank // self.cp_size  # 0 = uncond, 1 = cond (the reference's batch order, guiders.py:54)
+        # every rank must create every group (torch.distributed.new_group is collective over the world)
+        cp_groups = [dist.new_group(ranks=list(range(b * self.cp_size, (b + 1) * self.cp_size))) for b in range(2)]
+        pair_groups = [dist.new_group(ranks=[i, i + self.cp_size]) for i in range(self.cp_size)]
+        self.cp = ContextParallel(cp_groups[self.branch]) if self.cp_size > 1 else None
+        self.pair_group = pair_groups[rank % self.cp_size]
+
+    def gather_branches(self, v_mine):
+        """[1, ...] velocity of this rank's branch -> [2, ...] = (uncond, cond) on every rank."""
+        out = torch.empty((2,) + tuple(v_mine.shape[1:]), device=v_mine.device, dtype=v_mine.dtype)
+        dist.all_gather_into_tensor(out, v_mine.contiguous(), group=self.pair_group)  # group rank 0 = uncond half
+        return out

@@ -284,7 +284,12 @@ class WanVAE:
         self.scale = [self.mean, 1.0 / self.std]
         self.model = WanVAE_(z_dim=z_dim, **cfg)
         if vae_pth is not None:
-            self.model.load_state_dict(torch.load(vae_pth, map_location="cpu"), strict=False)
+            # the reference's load is mandatory and strict (wan_vae.py:607-616: load_state_dict(..., assign=True)); the
+            # parameter names are identical, so anything missing or unexpected is a wrong / partial checkpoint
+            self.model.load_state_dict(torch.load(vae_pth, map_location="cpu"), strict=True)
+        else:
+            import warnings
+            warnings.warn("scail_b200.wan_vae.WanVAE: vae_pth is None -> RANDOM weights (tests / benchmarks only)")
         self.model = self.model.eval().requires_grad_(False).to(device).to(torch.bfloat16)
 
     def encode(self, videos):

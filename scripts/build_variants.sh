@@ -4,14 +4,12 @@ cd "$(dirname "$0")/.."
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"
 build() { nvcc $F $2 -o scail_b200/libscail_b200_$1.so scail_b200/csrc/api.cu -lcudart & }
 rm -f scail_b200/libscail_b200_*.so
-build s1p0  "-DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x0u"
-build s4p0  "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x0u"
-build s1p25 "-DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x8888u"
-build s2p25 "-DSCAIL_ATT_P_SPLIT=2 -DSCAIL_ATT_POLY_MASK=0x8888u"
-build s4p25 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x8888u"
-build s4p37 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x9249u"
-build s4p50 "-DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0xAAAAu"
-build x4p25 "-DSCAIL_ATTN_EXPERIMENTS -DSCAIL_ATT_P_SPLIT=4 -DSCAIL_ATT_POLY_MASK=0x8888u"
-build x1p0 "-DSCAIL_ATTN_EXPERIMENTS -DSCAIL_ATT_P_SPLIT=1 -DSCAIL_ATT_POLY_MASK=0x0u"
+build p0  "-DSCAIL_ATT_POLY_MASK=0x0u"
+build p12 "-DSCAIL_ATT_POLY_MASK=0x8080u"
+build p25 "-DSCAIL_ATT_POLY_MASK=0x8888u"
+build p37 "-DSCAIL_ATT_POLY_MASK=0x9249u"
+build p50 "-DSCAIL_ATT_POLY_MASK=0xAAAAu"
+build x25 "-DSCAIL_ATTN_EXPERIMENTS -DSCAIL_ATT_POLY_MASK=0x8888u"
 wait
+nvcc $F -o scail_b200/libscail_b200.so scail_b200/csrc/api.cu -lcudart
 ls scail_b200/*.so

@@ -69,3 +69,51 @@ def test_context_parallel_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _hybrid_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scail_b200.parallel import HybridParallel
+        hp = HybridParallel()
+        assert hp.cp_size == world // 2 and hp.branch == rank // hp.cp_size
+        if hp.cp_size > 1:
+            assert hp.cp.size == hp.cp_size and hp.cp.rank == rank % hp.cp_size
+            # context-parallel token sharding inside this branch's half only
+            full = torch.arange(2 * 8 * 3, dtype=torch.float32).view(1, 16, 3) + 1000 * hp.branch
+            assert torch.equal(hp.cp.gather_tokens(hp.cp.shard_tokens(full), 16), full)
+        else:
+            assert hp.cp is None
+        # partner exchange: (uncond, cond) order on every rank, partner = same CP rank in the other half
+        v = torch.full((1, 4), float(10 * hp.branch + rank % hp.cp_size))
+        both = hp.gather_branches(v)
+        assert both.shape == (2, 4)
+        assert torch.equal(both[0], torch.full((4,), float(rank % hp.cp_size)))
+        assert torch.equal(both[1], torch.full((4,), float(10 + rank % hp.cp_size)))
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_hybrid(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_hybrid_cfg_parallel_world2():
+    _run_hybrid(2)
+
+
+def test_hybrid_cfg_x_cp_world4():
+    _run_hybrid(4)
