@@ -262,8 +262,6 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     if (residual) SCAIL_REQUIRE(ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
     CUtensorMap ta, tw;
     int rc;
-    if ((rc = make_tmap_2d(A, M, K, lda, GEMM_BM, GEMM_BK, &ta))) return rc;
-    if ((rc = make_tmap_2d(W, N, K, ldw, GEMM_BN, GEMM_BK, &tw))) return rc;
     GemmParams p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -275,11 +273,27 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     p.rows_per_batch = rows_per_batch > 0 ? (int)rows_per_batch : (int)M;
     p.epilogue = epilogue;
     static const int gm_env = getenv("SCAIL_GEMM_GROUP_M") ? atoi(getenv("SCAIL_GEMM_GROUP_M")) : 0;
+    static const int cg_env = getenv("SCAIL_GEMM_CG") ? atoi(getenv("SCAIL_GEMM_CG")) : 0;  // experiments: force 1 or 2
+    const int sms = sm_count();
+    SCAIL_REQUIRE(sms > 0, "gemm: no CUDA device");
+    // CTA-pair kernel for the big GEMMs (>= one 256-row tile pair per cluster); the 1-CTA kernel for short / skinny ones
+    const int64_t pair_tiles = blocks_for(M, 2 * GEMM_BM) * (int64_t)blocks_for(N, GEMM_BN);
+    const bool use_cg2 = cg_env ? cg_env == 2 : (M >= 2 * GEMM_BM && pair_tiles >= sms / 2);
+    if (use_cg2) {
+        if ((rc = make_tmap_2d(A, M, K, lda, 128, GEMM_BK, &ta))) return rc;
+        if ((rc = make_tmap_2d(W, N, K, ldw, 128, GEMM_BK, &tw))) return rc;
+        p.group_m = gm_env > 0 ? gm_env : 12;  // in 256-row pairs
+        if ((rc = set_smem(gemm_bf16_cg2_kernel, GEMM2_SMEM_BYTES))) return rc;
+        int grid = (int)(2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1));
+        gemm_bf16_cg2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ta, tw, p);
+        SCAIL_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if ((rc = make_tmap_2d(A, M, K, lda, GEMM_BM, GEMM_BK, &ta))) return rc;
+    if ((rc = make_tmap_2d(W, N, K, ldw, GEMM_BN, GEMM_BK, &tw))) return rc;
     p.group_m = gm_env > 0 ? gm_env : 24;
     if ((rc = set_smem(gemm_bf16_kernel, GEMM_SMEM_BYTES))) return rc;
     const int num_tiles = blocks_for(M, GEMM_BM) * blocks_for(N, GEMM_BN);
-    const int sms = sm_count();
-    SCAIL_REQUIRE(sms > 0, "gemm: no CUDA device");
     const int grid = num_tiles < sms ? num_tiles : sms;
     gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ta, tw, p);
     SCAIL_CHECK_CUDA(cudaGetLastError());

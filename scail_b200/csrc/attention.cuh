@@ -5,8 +5,7 @@
 //
 // One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles that ping-pong on the
 // tensor core.  Roles (12 warps = 3 warpgroups, registers re-split with setmaxnreg):
-//   warps 0-3  softmax warpgroup A: score columns  0..63  of BOTH Q tiles (thread = row, TMEM lane = 32*(warp%4)+lane)
-//   warps 4-7  softmax warpgroup B: score columns 64..127 of BOTH Q tiles
+//   warps 0-3  softmax warpgroup for Q tile 0      warps 4-7  softmax warpgroup for Q tile 1
 //   warp  8    TMA producer (Q once, K/V rings)     warp  9    tcgen05.mma issuer + TMEM owner   (10, 11 idle)
 // The MMA warp keeps its control flow warp-uniform (all lanes wait on the mbarriers; descriptors are computed in
 // uniform registers) and only the tcgen05 instructions are issued by the elected lane.
@@ -19,21 +18,14 @@
 //   O += P V  : UMMA 128x128x16, A from TMEM, B = V tile read MN-major straight from its [kv, d] layout (full rate).
 // Because P aliases S, one Q tile's loop-carried chain is  S -> softmax -> P -> PV -> next QK^T -> S, and the step time is
 // max(2048 cycles of UMMA, softmax latency + the part of PV + QK^T that cannot start before the last P column exists).
-// Measured with clock64 traces (scripts/trace_attn.py): with one warpgroup per Q tile the softmax latency of a tile is ~1530
-// cycles and the step is chain-bound at ~2800 cycles while the UMMA skeleton alone sustains ~2230.  Three things shorten
-// the chain:
-//   * BOTH warpgroups work on the SAME tile, each on one 64-column half of its rows (the row maximum is combined through
-//     shared memory behind a 64-thread named barrier per warp pair), then both move to the other tile: the per-tile
-//     softmax latency halves while each warpgroup does the same work per step;
-//   * P is handed over in 4 groups of 32 keys with one mbarrier each, so the PV UMMAs of the first groups run while
-//     the later exponentials are still being computed (only the last groups' k-steps stay on the chain);
+// Two things shorten that chain:
+//   * P is handed over in ATT_P_SPLIT column groups with one mbarrier each, so the PV UMMAs of the first groups run while
+//     the later exponentials are still being computed (only the last group's k-steps stay on the chain);
 //   * a fraction of the exponentials (ATT_POLY_MASK) runs as a Cody-Waite + cubic polynomial on the FMA pipe: MUFU.EX2
 //     (16/clk/SM) alone needs 1024 cycles per 128x128 tile.
 // Online softmax keeps a (possibly stale) running max; O is rescaled only when the max grew by > 2^8 (S full implies the
 // previous PV of that tile has completed, so the read-modify-write of O cannot race the tensor core).
 #pragma once
-#include <type_traits>
-
 #include "sm100.cuh"
 
 #ifdef SCAIL_ATTN_EXPERIMENTS
@@ -48,7 +40,10 @@
 #define SCAIL_ATT_POLY_MASK 0x8888u  // bit c set: column pair c of every 16-pair chunk uses the FMA-pipe exp2 (25 %)
 #endif
 #ifndef SCAIL_ATT_K_STAGES
-#define SCAIL_ATT_K_STAGES 2
+#define SCAIL_ATT_K_STAGES 3
+#endif
+#ifndef SCAIL_ATT_P_SPLIT
+#define SCAIL_ATT_P_SPLIT 4  // P hand-over groups per tile: 1, 2, 4 = equal groups of 128 / SPLIT keys; 3 = two groups of 96 + 32 keys
 #endif
 
 namespace scail {
@@ -58,14 +53,18 @@ constexpr int ATT_BQ = 128;   // rows per Q tile (2 tiles per CTA)
 constexpr int ATT_BKV = 128;  // keys per K/V tile
 constexpr int ATT_K_STAGES = SCAIL_ATT_K_STAGES;
 constexpr int ATT_V_STAGES = 2;
-constexpr int ATT_P_SPLIT = 4;  // P hand-over groups per tile: group = chunk * 2 + warpgroup, 32 keys each
+constexpr int ATT_P_MODE = SCAIL_ATT_P_SPLIT;
+constexpr int ATT_P_SPLIT = ATT_P_MODE == 3 ? 2 : ATT_P_MODE;  // number of hand-over groups (mbarriers) per tile
+// last 32-key chunk (0..3) of hand-over group g, and the group a chunk belongs to
+__host__ __device__ constexpr int att_group_last_chunk(int g) { return ATT_P_MODE == 3 ? (g == 0 ? 2 : 3) : (g + 1) * (4 / ATT_P_SPLIT) - 1; }
+__host__ __device__ constexpr int att_chunk_group(int ch) { return ATT_P_MODE == 3 ? (ch < 3 ? 0 : 1) : ch / (4 / ATT_P_SPLIT); }
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: one 128x128 bf16 tile (two 64-column halves)
 constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
 constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax0, softmax1, {TMA, MMA, 2 idle warps}
 constexpr uint32_t ATT_POLY_MASK = SCAIL_ATT_POLY_MASK;
-constexpr int ATT_XCHG_BYTES = 2 * 2 * 128 * 4;  // row-max / row-sum exchange between the warpgroups: [tile][half][row] fp32
-constexpr int ATT_SMEM_BYTES = (2 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 1024 + 256 + ATT_XCHG_BYTES;
+constexpr int ATT_SMEM_BYTES = (2 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 1024 + 256;
 static_assert(ATT_SMEM_BYTES <= 232448, "attention: shared memory budget");
+static_assert(ATT_P_MODE >= 1 && ATT_P_MODE <= 4, "attention: P split");
 
 struct AttnParams {
     __nv_bfloat16* out;  // [B*q_rows_per_batch, ldo]; head h written at columns [h*128, h*128+128)
@@ -103,49 +102,44 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&src)[32], uint64_t sc
     }
 }
 
-// One 128x64 half of a score tile for one softmax warp (thread = row; the partner warp of the other warpgroup owns the other
-// 64 columns of the same rows): TMEM S -> row max, combined with the partner's through `xchg` -> lazy O rescale (this warp's
-// 64 O columns) -> exp2 -> bf16 P back into TMEM in two 32-key groups.  MASK = this is the partial last KV tile.
-//   s_tmem   : this warp's 64 S columns          p_tmem : where its 32 packed P columns go (inside S columns [0,64))
-//   o_tmem   : this warp's 64 O columns          xchg_mine / xchg_other : this row's slot of the own / partner half
+// One 128x128 score tile of one softmax warp (thread = row): TMEM S -> running max (lazy O rescale) -> exp2 ->
+// bf16 P back into TMEM, handed to the MMA warp in ATT_P_SPLIT groups.  MASK = this is the partial last KV tile.
 template <bool MASK>
-__device__ __forceinline__ void softmax_half(uint32_t s_tmem, uint32_t p_tmem, uint32_t o_tmem, float scale_log2, int valid, int j,
-                                             float& m_run, float& l_run, uint32_t bar_p_c0, uint32_t bar_p_c1, float* xchg_mine,
-                                             const float* xchg_other, int pair_bar) {
-    uint32_t sa[32], sb[32];
-    tmem_ld_32x32(s_tmem + 0, sa);
-    tmem_ld_32x32(s_tmem + 32, sb);
+__device__ __forceinline__ void softmax_tile(uint32_t s_tmem, uint32_t o_tmem, float scale_log2, int valid, int j,
+                                             float& m_run, float& l_run, uint32_t bar_pfull0) {
+    uint32_t s0[32], s1[32], s2[32], s3[32];
+    tmem_ld_32x32(s_tmem + 0, s0);
+    tmem_ld_32x32(s_tmem + 32, s1);
+    tmem_ld_32x32(s_tmem + 64, s2);
+    tmem_ld_32x32(s_tmem + 96, s3);
     tmem_ld_wait();
     if constexpr (MASK) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-            if (c >= valid) sa[c] = 0xff800000u;
-            if (c + 32 >= valid) sb[c] = 0xff800000u;
+            if (c >= valid) s0[c] = 0xff800000u;
+            if (c + 32 >= valid) s1[c] = 0xff800000u;
+            if (c + 64 >= valid) s2[c] = 0xff800000u;
+            if (c + 96 >= valid) s3[c] = 0xff800000u;
         }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(sa[c]), __uint_as_float(sa[c + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(sa[c + 2]), __uint_as_float(sa[c + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(sb[c]), __uint_as_float(sb[c + 1]));
-        mx3 = fmax3(mx3, __uint_as_float(sb[c + 2]), __uint_as_float(sb[c + 3]));
+    for (int c = 0; c < 32; c += 2) {
+        mx0 = fmax3(mx0, __uint_as_float(s0[c]), __uint_as_float(s0[c + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s1[c]), __uint_as_float(s1[c + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(s2[c]), __uint_as_float(s2[c + 1]));
+        mx3 = fmax3(mx3, __uint_as_float(s3[c]), __uint_as_float(s3[c + 1]));
     }
-    const float mx_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    *xchg_mine = mx_half;
-    // The partner has its S half in registers when it arrives here (tcgen05.wait::ld above), so after this barrier either
-    // warp may overwrite S columns [0,64) with P.  64 threads: this warp and warp +-4.
-    named_bar_sync(pair_bar, 64);
-    const float mx = fmaxf(mx_half, *xchg_other);
+    const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     const float m_new = fmaxf(m_run, mx * scale_log2);
-    const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf); identical in both warps of the pair
+    const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
     if (__any_sync(0xffffffffu, need)) {
         const float alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
         m_run = m_new;
         l_run *= alpha;
         if (j > 0) {
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint32_t o[32];
                 tmem_ld_32x32(o_tmem + c * 32, o);
                 tmem_ld_wait();
@@ -159,24 +153,24 @@ __device__ __forceinline__ void softmax_half(uint32_t s_tmem, uint32_t p_tmem, u
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
     uint64_t sum_a = 0ull, sum_b = 0ull;  // packed (0.f, 0.f)
     const bool lane0 = (threadIdx.x & 31) == 0;
-    {
-        uint32_t pk[16];
-        exp_chunk(sa, sc2, nm2, sum_a, sum_b, pk);
-        tmem_st_32x16(p_tmem, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane0) mbar_arrive(bar_p_c0);
+    // chunk CH = 32 keys = 16 packed P columns; after the last chunk of hand-over group g the warp arrives on bar_pfull0 + 8 * g
+#define SCAIL_ATT_P_CHUNK(SRC, CH)                                             \
+    {                                                                          \
+        uint32_t pk[16];                                                       \
+        exp_chunk(SRC, sc2, nm2, sum_a, sum_b, pk);                            \
+        tmem_st_32x16(s_tmem + (CH) * 16, pk);                                 \
+        if (att_group_last_chunk(att_chunk_group(CH)) == (CH)) {                \
+            tmem_st_wait();                                                    \
+            tc_fence_before();                                                 \
+            __syncwarp();                                                      \
+            if (lane0) mbar_arrive(bar_pfull0 + 8u * att_chunk_group(CH));    \
+        }                                                                      \
     }
-    {
-        uint32_t pk[16];
-        exp_chunk(sb, sc2, nm2, sum_a, sum_b, pk);
-        tmem_st_32x16(p_tmem + 16, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane0) mbar_arrive(bar_p_c1);
-    }
+    SCAIL_ATT_P_CHUNK(s0, 0)
+    SCAIL_ATT_P_CHUNK(s1, 1)
+    SCAIL_ATT_P_CHUNK(s2, 2)
+    SCAIL_ATT_P_CHUNK(s3, 3)
+#undef SCAIL_ATT_P_CHUNK
     float la, lb, lc, ld;
     unpack_f32x2(sum_a, la, lb);
     unpack_f32x2(sum_b, lc, ld);
@@ -207,7 +201,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     auto bar = [&](int i) { return bar_base + 8u * i; };
     const uint32_t tmem_slot = bar_base + 8u * B_COUNT;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float* xchg = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));  // [tile][half][row]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -309,26 +302,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
             }
         };
-        // PV of one tile: hand-over group grp = chunk * 2 + warpgroup covers keys [64 * wg + 32 * chunk, +32) = UMMA k-steps
-        // 4 * wg + 2 * chunk and the next one; its two UMMAs are issued as soon as that group of P has been handed over
-        // (k-step order is irrelevant for the accumulation).
+        // PV of one tile: group g's k-steps are issued as soon as the softmax warpgroup has handed that group of P over
         auto issue_pv = [&](int tile, int vs, uint32_t parity, bool acc) {
             const uint32_t d = tmem_base + 256 + tile * 128;
             const uint32_t a = tmem_base + tile * 128;  // P aliases S columns [0,64)
             const uint64_t vb = v_desc0 + vs * STAGE_STEP;
 #pragma unroll
-            for (int grp = 0; grp < ATT_P_SPLIT; ++grp) {
-                mbar_wait(bar(B_PFULL + tile * ATT_P_SPLIT + grp), parity, 23 + tile);
+            for (int g = 0; g < ATT_P_SPLIT; ++g) {
+                mbar_wait(bar(B_PFULL + tile * ATT_P_SPLIT + g), parity, 23 + tile);
                 tc_fence_after();
 #ifdef SCAIL_ATTN_EXPERIMENTS
                 if (p.debug == 6) continue;
 #endif
                 if (leader) {
+                    // group g feeds the 16-key UMMA k-steps of its 32-key chunks (2 per chunk)
+                    const int k_lo = g == 0 ? 0 : 2 * (att_group_last_chunk(g - 1) + 1), k_hi = 2 * (att_group_last_chunk(g) + 1);
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int k = 4 * (grp & 1) + 2 * (grp >> 1) + kk;
+                    for (int k = k_lo; k < k_hi; ++k) {
                         // 16 kv rows per step = 2048 B inside each 64-column half; halves are 16 KB apart (LBO)
-                        umma_ts(d, a + k * 8, vb + k * (2048 >> 4), idesc_pv, acc || grp != 0 || kk != 0);
+                        umma_ts(d, a + k * 8, vb + k * (2048 >> 4), idesc_pv, acc || k != 0);
                     }
                 }
             }
@@ -378,102 +370,76 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     } else if (warp < 8) {
         // ===================== softmax warpgroups (+ O rescale + epilogue) =====================
         setmaxnreg_inc<208>();
-        const int wg = warp >> 2;   // column half: 0 -> score / output columns 0..63, 1 -> 64..127
-        const int sub = warp & 3;   // TMEM sub-partition = rows [32 * sub, 32 * sub + 32) of either Q tile
-        const int row = sub * 32 + lane;
+        const int tile = warp >> 2;  // 0 or 1
+        const int sub = warp & 3;
         const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-        const int pair_bar = 1 + sub;  // named barrier shared with the partner warp (warp ^ 4)
-        float m_run[2] = {-INFINITY, -INFINITY};  // running max per Q tile, already multiplied by scale_log2
-        float l_run[2] = {0.f, 0.f};              // partial row sums over this warp's column half
+        const uint32_t s_tmem = tmem_base + lane_off + tile * 128;
+        const uint32_t o_tmem = tmem_base + lane_off + 256 + tile * 128;
+        const uint32_t bar_p0 = bar(B_PFULL + tile * ATT_P_SPLIT);
+        float m_run = -INFINITY;  // running max, already multiplied by scale_log2
+        float l_run = 0.f;
         const int n_full = p.kv_len / ATT_BKV;  // full tiles; an optional partial tile follows (peeled: no per-iteration branch)
-        auto half_step = [&](auto mask_tag, int tile, int j, int valid_cols) {
-            constexpr bool MASK = decltype(mask_tag)::value;
-            const uint32_t s_tmem = tmem_base + lane_off + tile * 128 + wg * 64;
-            const uint32_t p_tmem = tmem_base + lane_off + tile * 128 + wg * 32;
-            const uint32_t o_tmem = tmem_base + lane_off + 256 + tile * 128 + wg * 64;
-            softmax_half<MASK>(s_tmem, p_tmem, o_tmem, p.scale_log2, valid_cols, j, m_run[tile], l_run[tile],
-                               bar(B_PFULL + tile * ATT_P_SPLIT + wg), bar(B_PFULL + tile * ATT_P_SPLIT + 2 + wg),
-                               xchg + (tile * 2 + wg) * 128 + row, xchg + (tile * 2 + (wg ^ 1)) * 128 + row, pair_bar);
-        };
         for (int j = 0; j < n_full; ++j) {
 #ifdef SCAIL_ATTN_EXPERIMENTS
             const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
 #endif
-#pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-                if (tile == 0) { SCAIL_ATTN_TRACE(j * 8 + 4); }
-                mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
-                if (tile == 0) { SCAIL_ATTN_TRACE(j * 8 + 5); }
-                tc_fence_after();
+            SCAIL_ATTN_TRACE(j * 8 + 4);
+            mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
+            SCAIL_ATTN_TRACE(j * 8 + 5);
+            tc_fence_after();
 #ifdef SCAIL_ATTN_EXPERIMENTS
-                if (p.debug == 1 || p.debug >= 5) {  // pipeline only: no TMEM reads, no math
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(bar(B_PFULL + tile * ATT_P_SPLIT + wg));
-                        mbar_arrive(bar(B_PFULL + tile * ATT_P_SPLIT + 2 + wg));
-                    }
-                    l_run[tile] = 1.f;
-                    continue;
-                }
-#endif
-                half_step(std::false_type{}, tile, j, 64);
-                if (tile == 0) { SCAIL_ATTN_TRACE(j * 8 + 6); }
+            if (p.debug == 1 || p.debug >= 5) {  // pipeline only: no TMEM reads, no math
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    for (int g = 0; g < ATT_P_SPLIT; ++g) mbar_arrive(bar_p0 + 8u * g);
+                l_run = 1.f;
+                continue;
             }
+#endif
+            softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, ATT_BKV, j, m_run, l_run, bar_p0);
+            SCAIL_ATTN_TRACE(j * 8 + 6);
         }
         if (n_full * ATT_BKV < p.kv_len) {  // partial last KV tile: masked instantiation
-            const int valid = p.kv_len - n_full * ATT_BKV - wg * 64;  // valid columns inside this warp's half (may be <= 0)
-#pragma unroll
-            for (int tile = 0; tile < 2; ++tile) {
-                mbar_wait(bar(B_SFULL + tile), n_full & 1, 32 + tile);
-                tc_fence_after();
-                half_step(std::true_type{}, tile, n_full, valid);
-            }
-        }
-        // ---- epilogue: O / l -> bf16 -> global; the two column halves of a row exchange their partial sums ----
-        named_bar_sync(pair_bar, 64);  // the partner has consumed this warp's last row-max slots
-#pragma unroll
-        for (int tile = 0; tile < 2; ++tile) xchg[(tile * 2 + wg) * 128 + row] = l_run[tile];
-        named_bar_sync(pair_bar, 64);
-#pragma unroll 1
-        for (int tile = 0; tile < 2; ++tile) {
-            mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);
+            mbar_wait(bar(B_SFULL + tile), n_full & 1, 32 + tile);
             tc_fence_after();
-            const float l_tot = l_run[tile] + xchg[(tile * 2 + (wg ^ 1)) * 128 + row];
-            const int qi = q0 + tile * ATT_BQ + row;
-            const bool row_ok = qi < p.q_len;
-            const float inv_l = 1.0f / l_tot;
-            const uint32_t o_tmem = tmem_base + lane_off + 256 + tile * 128 + wg * 64;
-            __nv_bfloat16* orow = p.out + (static_cast<int64_t>(batch) * p.q_batch_rows + qi) * p.ldo + head * ATT_D + wg * 64;
+            softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, p.kv_len - n_full * ATT_BKV, n_full, m_run, l_run, bar_p0);
+        }
+        // ---- epilogue: O / l -> bf16 -> global ----
+        mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);
+        tc_fence_after();
+        const int qi = q0 + tile * ATT_BQ + sub * 32 + lane;
+        const bool row_ok = qi < p.q_len;
+        const float inv_l = 1.0f / l_run;
+        __nv_bfloat16* orow = p.out + (static_cast<int64_t>(batch) * p.q_batch_rows + qi) * p.ldo + head * ATT_D;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld_32x32(o_tmem + c * 32, o);
-                tmem_ld_wait();
-                if (row_ok) {
+        for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_tmem + c * 32, o);
+            tmem_ld_wait();
+            if (row_ok) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float f[8];
+                for (int g = 0; g < 4; ++g) {
+                    float f[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(o[g * 8 + k]) * inv_l;
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + g * 8);
-                        if (p.accumulate) {
-                            uint4 prev = *dst;
-                            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+                    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(o[g * 8 + k]) * inv_l;
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32 + g * 8);
+                    if (p.accumulate) {
+                        uint4 prev = *dst;
+                        const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                float2 t = unpack_bf16(pw[k]);
-                                f[2 * k] += t.x;
-                                f[2 * k + 1] += t.y;
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            float2 t = unpack_bf16(pw[k]);
+                            f[2 * k] += t.x;
+                            f[2 * k + 1] += t.y;
                         }
-                        uint4 ov;
-                        ov.x = pack_bf16(f[0], f[1]);
-                        ov.y = pack_bf16(f[2], f[3]);
-                        ov.z = pack_bf16(f[4], f[5]);
-                        ov.w = pack_bf16(f[6], f[7]);
-                        *dst = ov;
                     }
+                    uint4 ov;
+                    ov.x = pack_bf16(f[0], f[1]);
+                    ov.y = pack_bf16(f[2], f[3]);
+                    ov.z = pack_bf16(f[4], f[5]);
+                    ov.w = pack_bf16(f[6], f[7]);
+                    *dst = ov;
                 }
             }
         }

@@ -134,6 +134,45 @@ def sample_long(model, x, cond, uc, tile_indices, num_steps=50, shift_scale=5.0,
     return x
 
 
+class GraphedStep:
+    """One sampler step with the whole CFG batch-2 DiT forward (~780 kernel launches of libscail_b200.so)
+    captured ONCE in a CUDA graph and replayed per step: 3 host launches per step (timestep fill, graph replay, CFG+Euler)
+    instead of ~780, and none of the reference's per-layer host syncs (sat/transformer_defaults.py:56-57) by construction.
+    The latent `x`, the timestep vector and the conditioning tensors are static buffers owned by this object; results are
+    bit-identical to `sampler_step` (same kernels, same order).  Single-GPU path (NCCL collectives are not captured)."""
+
+    def __init__(self, model, x, cond, uc, scale=4.0):
+        if getattr(model.mixins["adaln_layer"], "cp", None) is not None:
+            raise NotImplementedError("GraphedStep captures the single-GPU forward; use sampler_step under context parallelism")
+        self.model, self.scale = model, scale
+        self.x = x  # fp32 [1,t,16,h,w], updated in place every step
+        dev = x.device
+        self.ts = torch.zeros(2, device=dev, dtype=torch.float32)
+        self.ctx = prepare_context(cond, uc)
+        self.kw = dict(y=None, ref_concat=cond["ref_concat"], concat_smpl_render=cond["concat_smpl_render"],
+                       image_clip_features=cond["image_clip_features"], concat_images=cond.get("concat_images"))
+        assert ops.ATTN_EVENTS is None, "event timing of individual launches cannot be captured"
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():  # warm-up on the capture stream: workspaces and TMA descriptors exist
+            self._forward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES
+        with torch.cuda.graph(self.graph, stream=side), torch.no_grad():
+            self.v = self._forward()
+        self.kernels_in_graph = ops.LAUNCHES - n0
+
+    def _forward(self):
+        return self.model(torch.cat([self.x, self.x], 0), timesteps=self.ts, context=self.ctx, **self.kw).contiguous()
+
+    def __call__(self, sigma, next_sigma):
+        self.ts.fill_(float(sigma) * 1000.0)
+        self.graph.replay()
+        return ops.cfg_euler_(self.x, self.v, self.scale, float(next_sigma) - float(sigma))
+
+
 class HostStep:
     """End-to-end step through host buffers: pinned host -> device copies of the step's inputs, one sampler
     step, device -> pinned host copy of the updated latent.  This is what bench.py's `e2e` times."""

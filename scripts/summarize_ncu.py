@@ -1,5 +1,5 @@
 """Summarise ncu outputs (run here, no GPU needed):  python scripts/summarize_ncu.py <tag>
-Reads gpurun_out/launches_<tag>.csv and gpurun_out/{attn,gemm}_<tag>.ncu-rep, writes profiles/<tag>_ncu_summary.md"""
+Reads gpurun_out/launches_<tag>.csv and gpurun_out/{attn,gemm,rows,conv}_<tag>.ncu-rep, writes profiles/<tag>_ncu_summary.md"""
 import collections
 import csv
 import io
@@ -42,7 +42,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg.per_second",
         "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
         "lts__t_sector_hit_rate.pct", "sm__cycles_active.avg"]
-for k in ("attn", "gemm", "conv"):
+for k in ("attn", "gemm", "rows", "conv"):
     try:
         txt = subprocess.run(["ncu", "-i", f"gpurun_out/{k}_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))

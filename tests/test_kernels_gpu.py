@@ -114,6 +114,30 @@ def test_rmsnorm_rope(D, heads):
     assert torch.equal(qkv[:, 2 * D:], v_before)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(2048, 2560, 512, 0), (2176, 2304, 640, 2), (4100, 1288, 256, 1), (256, 18944, 128, 3)])
+def test_gemm_cta_pair_kernel(M, N, K, epi):
+    """Shapes with >= 74 tile pairs take the cta_group::2 kernel (256 x 256 tiles over two CTAs): ragged M / N edges,
+    every fused epilogue, against an fp32 reference."""
+    from scail_b200 import ops
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2) * 0.05, rnd(N, seed=3)
+    ref = a.float() @ w.float().t() + b.float()
+    kw = {}
+    rpb = 1024
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    if epi in (2, 3):
+        res = rnd(M, N, seed=4)
+        kw = dict(residual=res.clone())
+        if epi == 2:
+            gate = rnd((M + rpb - 1) // rpb, N, seed=5)
+            kw.update(gate=gate, rows_per_batch=rpb)
+            ref = ref * gate.float().repeat_interleave(rpb, 0)[:M]
+        ref = ref + res.float()
+    out = ops.gemm(a, w, b, epilogue=epi, **kw)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 4e-3, rel(out, ref)
+
+
 @pytest.mark.parametrize("B,H,nq,nkv", [(1, 1, 256, 128), (1, 2, 256, 256), (2, 2, 384, 384), (1, 2, 300, 257),
                                         (2, 3, 512, 1000), (1, 1, 128, 4096), (1, 1, 128, 64), (1, 2, 256, 40),
                                         (1, 1, 256, 191), (2, 1, 130, 193), (1, 2, 256, 320)])
@@ -219,8 +243,8 @@ def test_error_paths_return_codes_not_crashes():
         ops.gemm(a, w, epilogue=17)
     with pytest.raises(RuntimeError, match="gate/residual required"):
         ops.gemm(a, w, epilogue=ops.EPI_BIAS_GATE_RES)
-    x = rnd(2, 4, 384)
-    with pytest.raises(RuntimeError, match="multiple of 256"):
+    x = rnd(2, 4, 388)
+    with pytest.raises(RuntimeError, match="multiple of 8"):
         ops.ln_modulate(x)
     with pytest.raises(RuntimeError, match="unsupported channel count"):
         ops.rmsnorm_cl(rnd(4, 40), rnd(40))
