@@ -39,7 +39,7 @@ import torch  # noqa: E402
 D, F, HEADS, LAYERS, TEXT_DIM = 5120, 13824, 40, 40, 4096
 T_LAT, H_LAT, W_LAT = 21, 64, 64  # 512x512, 81 frames
 N_TEXT, N_CLIP = 512, 257
-NCU_ATTN_DRAM_BYTES = 1.727272e9 + 0.562356e9  # per self-attention launch (b=2, 40 heads, N=27904), profiles/r01b_ncu_summary.md
+NCU_ATTN_DRAM_BYTES = 1.723713e9 + 0.555318e9  # per self-attention launch (b=2, 40 heads, N=27904), profiles/r02_ncu_summary.md
 
 
 def seq_len(t=None, h=None, w=None):
@@ -358,6 +358,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (some images default to NCCL_DEBUG=VERSION)
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(dev, layers=args.layers)
     plan = None
@@ -463,7 +464,7 @@ def main():
                         "frac": attn_flops / attn_avg / 1e9 / peaks["bf16_tflops_sustained"] if attn_avg else None,
                         "traffic": NCU_ATTN_DRAM_BYTES if (world == 1 and args.latent is None) else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this "
-                                          "launch shape (profiles/r01b_ncu_summary.md); algorithmic Q+K+V+O bytes = 2.286e9",
+                                          "launch shape (profiles/r02_ncu_summary.md); algorithmic Q+K+V+O bytes = 2.286e9",
                         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                         "algorithmic_flops_per_launch": attn_flops, "avg_launch_ms": attn_avg,
                         "share_of_step": sum(attn_ms) / args.steps / ms if attn_ms else None}}

@@ -274,6 +274,8 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     p.epilogue = epilogue;
     static const int gm_env = getenv("SCAIL_GEMM_GROUP_M") ? atoi(getenv("SCAIL_GEMM_GROUP_M")) : 0;
     static const int cg_env = getenv("SCAIL_GEMM_CG") ? atoi(getenv("SCAIL_GEMM_CG")) : 0;  // experiments: force 1 or 2
+    static const int hint_env = getenv("SCAIL_GEMM_L2_HINTS") ? atoi(getenv("SCAIL_GEMM_L2_HINTS")) : 1;
+    p.l2_hints = hint_env;
     const int sms = sm_count();
     SCAIL_REQUIRE(sms > 0, "gemm: no CUDA device");
     // CTA-pair kernel for the big GEMMs (>= one 256-row tile pair per cluster); the 1-CTA kernel for short / skinny ones

@@ -35,6 +35,7 @@ struct GemmParams {
     int rows_per_batch;
     int epilogue;
     int group_m;  // rasterisation: m-blocks per L2 group
+    int l2_hints; // CTA-pair kernel: 0 = none, 1 = A evict_last, 2 = A evict_last + W evict_first
 };
 
 constexpr int GEMM_BM = 128;
@@ -321,6 +322,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy encodings: evict_last keeps the operand block that is re-read by the
+// following waves resident while the other operand streams through L2)
+constexpr uint64_t TMA_L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t TMA_L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t TMA_L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1,
+                                                      uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -387,8 +400,14 @@ gemm_bf16_cg2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
                     if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * GEMM2_STAGE_BYTES);
                     const uint32_t lead_full = cluster_map_addr(full_bar(stage), 0);  // the leader's barrier collects both CTAs' bytes
-                    tma_load_2d_pair(sa, &tmap_a, lead_full, kb * GEMM_BK, m_row);
-                    tma_load_2d_pair(sa + GEMM2_A_BYTES, &tmap_w, lead_full, kb * GEMM_BK, n_row);
+                    if (p.l2_hints) {  // A rows of this m-group are re-read by every following wave of the group; W streams
+                        tma_load_2d_pair_hint(sa, &tmap_a, lead_full, kb * GEMM_BK, m_row, TMA_L2_EVICT_LAST);
+                        tma_load_2d_pair_hint(sa + GEMM2_A_BYTES, &tmap_w, lead_full, kb * GEMM_BK, n_row,
+                                              p.l2_hints == 2 ? TMA_L2_EVICT_FIRST : TMA_L2_EVICT_NORMAL);
+                    } else {
+                        tma_load_2d_pair(sa, &tmap_a, lead_full, kb * GEMM_BK, m_row);
+                        tma_load_2d_pair(sa + GEMM2_A_BYTES, &tmap_w, lead_full, kb * GEMM_BK, n_row);
+                    }
                     if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }

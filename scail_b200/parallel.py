@@ -51,13 +51,14 @@ class ContextParallel:
         s = slice(self.rank * n_local, (self.rank + 1) * n_local)
         return cos[s], sin[s]
 
-    def kv_buffer(self, B, n_local, d, device, dtype=torch.bfloat16):
-        """[B, P, N/P, 2d]: batch-major so that, after the gather, batch b's keys/values are the contiguous
-        [P*N/P, 2d] matrix the attention kernel addresses with kv_batch_rows = N."""
+    def kv_buffer(self, B, n_local, d, device, dtype=torch.bfloat16, width=None, tag="kv"):
+        """[B, P, N/P, width] (default width 2d = K | V): batch-major so that, after the gather, batch b's keys/values are
+        the contiguous [P*N/P, width] matrix the attention kernel addresses with kv_batch_rows = N."""
+        width = 2 * d if width is None else width
         sid = torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
-        key = (B, n_local, d, str(device), dtype, sid)  # one buffer per stream (CFG branches run concurrently)
+        key = (tag, B, n_local, width, str(device), dtype, sid)  # one buffer per stream (CFG branches run concurrently)
         if key not in self._kv:
-            self._kv[key] = torch.empty(B, self.size, n_local, 2 * d, device=device, dtype=dtype)
+            self._kv[key] = torch.empty(B, self.size, n_local, width, device=device, dtype=dtype)
         return self._kv[key]
 
     def gather_kv(self, kvbuf, async_op=True):
@@ -87,23 +88,28 @@ class ContextParallel:
                                  "tokens must be sharded with shard_tokens() (or pass chunk_dim for pre-chunked latents)")
             cos_l, sin_l = self.rope_slice(cos, sin, n_local)
         w, bias = attn.query_key_value.weight, attn.query_key_value.bias
-        kvbuf = self.kv_buffer(B, n_local, d, dev)
-        for b in range(B):  # K,V projection straight into this rank's slot of the gather buffer
-            slot = kvbuf[b, self.rank]
-            ops.gemm(h2[b * n_local:(b + 1) * n_local], w[d:], bias[d:], out=slot)
+        # K and V travel separately so that the K gather is already in flight during the V (and Q) projection and the V gather
+        # during the Q projection: with one CFG branch per rank (HybridParallel) there is no second stream to hide it behind
+        kbuf = self.kv_buffer(B, n_local, d, dev, width=d, tag="k")
+        vbuf = self.kv_buffer(B, n_local, d, dev, width=d, tag="v")
+        for b in range(B):  # K projection + RMSNorm/RoPE straight into this rank's slot of the gather buffer
+            slot = kbuf[b, self.rank]
+            ops.gemm(h2[b * n_local:(b + 1) * n_local], w[d:2 * d], bias[d:2 * d], out=slot)
             ops.rmsnorm_rope(slot, n_local, d, [(0, wk)], cos_l, sin_l, eps=eps)
-        works = self.gather_kv(kvbuf, async_op=True)
+        works = self.gather_kv(kbuf, async_op=True)
+        for b in range(B):
+            ops.gemm(h2[b * n_local:(b + 1) * n_local], w[2 * d:], bias[2 * d:], out=vbuf[b, self.rank])
+        works += self.gather_kv(vbuf, async_op=True)
         qkey = (B * n_local, d, str(dev), torch.cuda.current_stream(dev).cuda_stream)
         if qkey not in self._q:
             self._q[qkey] = torch.empty(B * n_local, d, device=dev, dtype=torch.bfloat16)
         q = self._q[qkey]
-        ops.gemm(h2, w[:d], bias[:d], out=q)  # overlaps the all-gather
+        ops.gemm(h2, w[:d], bias[:d], out=q)  # overlaps the all-gathers
         ops.rmsnorm_rope(q, n_local, d, [(0, wq)], cos_l, sin_l, eps=eps)
         for wk_ in works:
             wk_.wait()
-        kv2 = kvbuf.view(B * P * n_local, 2 * d)
-        ops.attention(q, kv2[:, :d], kv2[:, d:], ctx, B, H, n_local, P * n_local, q_batch_rows=n_local,
-                      kv_batch_rows=P * n_local)
+        ops.attention(q, kbuf.view(B * P * n_local, d), vbuf.view(B * P * n_local, d), ctx, B, H, n_local, P * n_local,
+                      q_batch_rows=n_local, kv_batch_rows=P * n_local)
         return ctx
 
 
