@@ -195,6 +195,9 @@ def cpu_baseline(threads=None, budget_s=150.0):
             "extrapolation_factor": factor, "est_step_seconds": est_step_s}
 
 
+CPU_ARM_BUDGET_S = 180.0  # host seconds the timed steps of `--impl reference` may spend on full-N blocks
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -203,7 +206,7 @@ def run_reference_arm(args):
     for i in range(args.warmup + args.steps):
         # warm-up iterations use the reduced sample; the timed ones share ~3 minutes of host time, so the full-N block
         #  is used when its predicted cost fits and the FLOP-scaled reduced block otherwise (the line says which)
-        cb = cpu_baseline(budget_s=180.0 / max(args.steps, 1) if i >= args.warmup else 0.0)
+        cb = cpu_baseline(budget_s=CPU_ARM_BUDGET_S / max(args.steps, 1) if i >= args.warmup else 0.0)
         if i >= args.warmup:
             vals.append(cb)
     v = statistics.mean(c["value"] for c in vals)
@@ -241,12 +244,23 @@ def kernel_compare(dev):
         b = torch.randn(N, device=dev, dtype=torch.bfloat16)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         kw = dict(gate=torch.randn(2, N, device=dev, dtype=torch.bfloat16), residual=out, rows_per_batch=n) if epi == 2 else {}
-        ms = _time_cuda(lambda: ops.gemm(a, w, b, out=out, epilogue=epi, **kw), 5, 2)
-        ms_t = _time_cuda(lambda: torch.nn.functional.linear(a, w, b), 5, 2)
-        res["gemm_" + name] = {"ours_ms": round(ms, 3), "cublas_ms": round(ms_t, 3), "ours_tflops": round(2 * M * N * K / ms / 1e9, 1),
-                               "ours_over_cublas": round(ms_t / ms, 3),
-                               "note": "ours includes the fused bias" + ("+GELU" if epi == 1 else "+gate+residual" if epi == 2 else "")
-                                       + " epilogue; cuBLAS = F.linear (bias only)"}
+        ms = _time_cuda(lambda: ops.gemm(a, w, b, out=out, epilogue=epi, **kw), 20, 3)
+        ms_t = _time_cuda(lambda: torch.nn.functional.linear(a, w, b), 20, 3)
+        lin = torch.nn.functional.linear
+        if epi == 1:    # what the reference launches for the same math: F.linear then nn.GELU(tanh)
+            lib = lambda: torch.nn.functional.gelu(lin(a, w, b), approximate="tanh")
+        elif epi == 2:  # RowParallelLinear (matmul, + bias) then x + gate * y  (dit_video_crossattn_sc_xc.py:1036,1050)
+            g3, r3 = kw["gate"].view(2, 1, N), out.view(2, n, N)
+            lib = lambda: r3 + g3 * (lin(a, w) + b).view(2, n, N)
+        else:
+            lib = lambda: lin(a, w, b)
+        ms_l = _time_cuda(lib, 20, 3)
+        res["gemm_" + name] = {"ours_ms": round(ms, 3), "cublas_ms": round(ms_t, 3), "library_same_math_ms": round(ms_l, 3),
+                               "ours_tflops": round(2 * M * N * K / ms / 1e9, 1), "ours_over_cublas": round(ms_t / ms, 3),
+                               "ours_over_library_same_math": round(ms_l / ms, 3),
+                               "note": "ours = one launch incl. the fused bias" + ("+GELU" if epi == 1 else "+gate+residual" if epi == 2 else "")
+                                       + " epilogue; cublas_ms = F.linear alone; library_same_math_ms = F.linear plus the elementwise "
+                                         "ops the reference runs after it; 20 back-to-back launches each (power cap settled)"}
         del a, w, out
     qkv = torch.randn(M, 3 * D, device=dev, dtype=torch.bfloat16)
     out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)

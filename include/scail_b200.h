@@ -41,8 +41,10 @@ enum {
 };
 
 /* C[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W, C bf16 row-major with leading dims lda/ldw/ldc
- * (elements, multiples of 8).  bias [N] bf16 or NULL; gate [B, gate_stride] bf16 indexed by
- * row / rows_per_batch; residual [M, ldr] bf16.  c_fp32 != 0 writes float32 C instead.
+ * (elements, multiples of 8; ldc % 4 for a float32 C).  bias [N] bf16 or NULL; gate [B, gate_stride] bf16 indexed by
+ * row / rows_per_batch; residual [M, ldr] bf16.  c_fp32 != 0 writes float32 C instead.  C, bias, gate and residual must be
+ * 16-byte aligned (-1 otherwise).  Shapes with >= one 256x256 tile pair per SM pair run on the CTA-pair kernel
+ * (tcgen05 cta_group::2, cluster of 2 CTAs), the others on the single-CTA kernel; same numerics.
  * Replaces ColumnParallelLinear.forward / RowParallelLinear.forward (sat/mpu/layers.py:230-243,
  * :425-444) and nn.Linear / nn.Conv3d-as-GEMM call sites of the DiT. */
 int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
@@ -51,7 +53,7 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
 
 /* out = modulate(LayerNorm(x)) per row.  gamma/beta (bf16 [D]) and shift/scale (bf16 [B, mod_stride])
  * are optional (NULL).  Reads rows [in_row_offset, in_row_offset+rows_out) of each batch of
- * in_batch_rows rows; writes [B*rows_out, D] densely.  D % 256 == 0, D <= 5120.
+ * in_batch_rows rows; writes [B*rows_out, D] densely.  D % 8 == 0, D <= 5120.
  * Replaces layer.input_layernorm / post_attention_layernorm / post_cross_attention_layernorm /
  * norm_final + modulate (dit_video_crossattn_sc_xc.py:1031-1032, 1039, 1045-1046, 825, 760-761). */
 int scail_ln_modulate(const void* x, void* out, const void* gamma, const void* beta, const void* shift,

@@ -52,6 +52,7 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+                assert "import baseline" not in src and "from baseline" not in src, f  # the library-path arm is bench-only
 
 
 def test_rope_tables_bit_identical_to_oracle():
@@ -128,7 +129,7 @@ def test_bench_reference_arm_json_contract():
     import json
     import subprocess
     code = ("import sys, json; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0'];"
-            "import bench; bench.cpu_baseline.__defaults__=(3,16,16,None); bench.main()")
+            "import bench; bench.CPU_ARM_BUDGET_S=0.0; bench.main()")  # budget 0 -> the reduced 9x32x32 sample
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
