@@ -78,6 +78,21 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
                     int64_t kv_batch_rows, int64_t q_rows_total, int64_t kv_rows_total, float scale, int accumulate,
                     scail_stream_t stream);
 
+/* Context parallelism: attention over a SUBSET of the keys, to be merged later.  Keys are the rows
+ * [kv_off0, kv_off0 + kv_len0) and (optionally, kv_len1 > 0) [kv_off1, kv_off1 + kv_len1) of every batch of kv_batch_rows rows
+ * ("every shard but mine").  Writes the partial result normalised by its own row sum as float32 o32 [rows, ldo32] and
+ * state [rows * H] = (running max in log2 units, row sum) float2.  Same kernel as scail_attention.
+ * Replaces the all_to_all_4D + SDPA + all_to_all_4D sequence of UlyssesAttention.forward (sat/mpu/ulysses_attn_layer.py:41-110)
+ * together with scail_attention_merge. */
+int scail_attention_partial(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, float* o32,
+                            int64_t ldo32, void* state, int64_t B, int64_t H, int64_t q_len, int64_t kv_off0, int64_t kv_len0,
+                            int64_t kv_off1, int64_t kv_len1, int64_t q_batch_rows, int64_t kv_batch_rows, int64_t q_rows_total,
+                            int64_t kv_rows_total, float scale, scail_stream_t stream);
+/* out (bf16 [rows, ldo], head h at columns h*128..) = softmax-consistent combination of two partial results over disjoint key
+ * sets: (w_a O_a + w_b O_b) / (w_a + w_b), w_x = l_x 2^(m_x - max(m_a, m_b)). */
+int scail_attention_merge(const float* o32_a, const void* state_a, const float* o32_b, const void* state_b, void* out,
+                          int64_t ldo32, int64_t ldo, int64_t rows, int64_t H, scail_stream_t stream);
+
 /* mod[b, i] = emb[b, i] + param[i]  (shared-AdaLN modulation vectors, dit_video_crossattn_sc_xc.py:1025-1028, 823) */
 int scail_adaln_modulation(const void* emb, const void* param, void* out, int64_t B, int64_t n, scail_stream_t stream);
 int scail_silu(const void* x, void* out, int64_t n, scail_stream_t stream);

@@ -29,6 +29,9 @@ SIGNATURES = {
     "scail_rmsnorm_rope": [c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_p, c_i64, c_p, c_p, c_p, c_f, c_p],
     "scail_attention": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                         c_i64, c_i64, c_f, c_int, c_p],
+    "scail_attention_partial": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                c_i64, c_i64, c_i64, c_i64, c_i64, c_f, c_p],
+    "scail_attention_merge": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p],
     "scail_adaln_modulation": [c_p, c_p, c_p, c_i64, c_i64, c_p],
     "scail_silu": [c_p, c_p, c_i64, c_p],
     "scail_timestep_embedding": [c_p, c_p, c_i64, c_i64, c_p],
@@ -95,6 +98,8 @@ def lib():
     h.scail_last_error.restype = ctypes.c_char_p
     h.scail_last_error.argtypes = []
     for name, args in SIGNATURES.items():
+        if _VARIANT and not hasattr(h, name):
+            continue  # experiment builds (scripts/build_variants.sh) may predate an entry point
         fn = getattr(h, name)
         fn.argtypes = args
         fn.restype = c_int

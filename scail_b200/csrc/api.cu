@@ -341,17 +341,20 @@ int scail_rmsnorm_rope(void* buf, int64_t ld, int64_t rows, int64_t rows_per_bat
     return 0;
 }
 
-int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* out,
-                    int64_t ldo, int64_t B, int64_t H, int64_t q_len, int64_t kv_len, int64_t q_batch_rows,
-                    int64_t kv_batch_rows, int64_t q_rows_total, int64_t kv_rows_total, float scale, int accumulate,
-                    scail_stream_t stream) {
+static int attention_impl(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* out,
+                          int64_t ldo, int64_t B, int64_t H, int64_t q_len, int64_t kv_off0, int64_t kv_len0, int64_t kv_off1,
+                          int64_t kv_len1, int64_t q_batch_rows, int64_t kv_batch_rows, int64_t q_rows_total,
+                          int64_t kv_rows_total, float scale, int accumulate, float* o32, int64_t ldo32, void* state,
+                          scail_stream_t stream) {
     using namespace scail;
-    SCAIL_REQUIRE(Q && K && V && out, "attention: null operand");
-    SCAIL_REQUIRE(B > 0 && H > 0 && q_len > 0 && kv_len > 0, "attention: bad shape");
+    SCAIL_REQUIRE(Q && K && V && (out || o32), "attention: null operand");
+    SCAIL_REQUIRE(B > 0 && H > 0 && q_len > 0 && kv_len0 > 0 && kv_len1 >= 0 && kv_off0 >= 0 && kv_off1 >= 0, "attention: bad shape");
     SCAIL_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention: leading dims must be multiples of 8");
-    SCAIL_REQUIRE(aligned16(out), "attention: out must be 16-byte aligned");
-    SCAIL_REQUIRE(q_len <= q_batch_rows && kv_len <= kv_batch_rows && B * q_batch_rows <= q_rows_total + (q_batch_rows - q_len) &&
-                      B * kv_batch_rows <= kv_rows_total + (kv_batch_rows - kv_len),
+    SCAIL_REQUIRE(aligned16(out) && aligned16(o32), "attention: out must be 16-byte aligned");
+    SCAIL_REQUIRE((o32 == nullptr) == (state == nullptr) && (!o32 || (ldo32 % 4 == 0 && !accumulate)), "attention: o32 and state come together (ldo32 %% 4 == 0, no accumulate)");
+    SCAIL_REQUIRE(q_len <= q_batch_rows && kv_off0 + kv_len0 <= kv_batch_rows && kv_off1 + kv_len1 <= kv_batch_rows &&
+                      B * q_batch_rows <= q_rows_total + (q_batch_rows - q_len) &&
+                      (B - 1) * kv_batch_rows + (kv_len1 > 0 ? kv_off1 + kv_len1 : kv_off0 + kv_len0) <= kv_rows_total,
                   "attention: row extents inconsistent");
     CUtensorMap tq, tk, tv;
     int rc;
@@ -361,7 +364,9 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
     if ((rc = make_tmap_2d(V, kv_rows_total, cols, ldv, ATT_BKV, 64, &tv))) return rc;
     AttnParams p;
     p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
-    p.q_len = (int)q_len; p.kv_len = (int)kv_len; p.q_batch_rows = (int)q_batch_rows; p.kv_batch_rows = (int)kv_batch_rows;
+    p.q_len = (int)q_len; p.kv_len = (int)kv_len0; p.kv_off = (int)kv_off0; p.kv_off1 = (int)kv_off1; p.kv_len1 = (int)kv_len1;
+    p.q_batch_rows = (int)q_batch_rows; p.kv_batch_rows = (int)kv_batch_rows;
+    p.o32 = o32; p.ldo32 = ldo32; p.state = static_cast<float2*>(state); p.heads = (int)H;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.accumulate = accumulate;
     p.trace = g_attn_trace;
@@ -370,6 +375,36 @@ int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, cons
     if ((rc = set_smem(attention_fwd_kernel, ATT_SMEM_BYTES))) return rc;
     dim3 grid(blocks_for(q_len, 2 * ATT_BQ), (unsigned)H, (unsigned)B);
     attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int scail_attention(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, void* out,
+                    int64_t ldo, int64_t B, int64_t H, int64_t q_len, int64_t kv_len, int64_t q_batch_rows,
+                    int64_t kv_batch_rows, int64_t q_rows_total, int64_t kv_rows_total, float scale, int accumulate,
+                    scail_stream_t stream) {
+    return attention_impl(Q, ldq, K, ldk, V, ldv, out, ldo, B, H, q_len, 0, kv_len, 0, 0, q_batch_rows, kv_batch_rows, q_rows_total,
+                          kv_rows_total, scale, accumulate, nullptr, 0, nullptr, stream);
+}
+
+int scail_attention_partial(const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, float* o32,
+                            int64_t ldo32, void* state, int64_t B, int64_t H, int64_t q_len, int64_t kv_off0, int64_t kv_len0,
+                            int64_t kv_off1, int64_t kv_len1, int64_t q_batch_rows, int64_t kv_batch_rows, int64_t q_rows_total,
+                            int64_t kv_rows_total, float scale, scail_stream_t stream) {
+    SCAIL_REQUIRE(o32 && state, "attention_partial: null operand");
+    return attention_impl(Q, ldq, K, ldk, V, ldv, nullptr, 8, B, H, q_len, kv_off0, kv_len0, kv_off1, kv_len1, q_batch_rows,
+                          kv_batch_rows, q_rows_total, kv_rows_total, scale, 0, o32, ldo32, state, stream);
+}
+
+int scail_attention_merge(const float* o32_a, const void* state_a, const float* o32_b, const void* state_b, void* out,
+                          int64_t ldo32, int64_t ldo, int64_t rows, int64_t H, scail_stream_t stream) {
+    SCAIL_REQUIRE(o32_a && state_a && o32_b && state_b && out && rows > 0 && H > 0, "attention_merge: bad args");
+    SCAIL_REQUIRE(ldo32 % 4 == 0 && ldo % 4 == 0 && aligned16(o32_a) && aligned16(o32_b) && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+                  "attention_merge: alignment");
+    const int64_t warps = rows * H;
+    scail::attn_merge_kernel<<<blocks_for(warps, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        o32_a, static_cast<const float2*>(state_a), o32_b, static_cast<const float2*>(state_b), static_cast<__nv_bfloat16*>(out),
+        ldo32, ldo, rows, (int)H);
     SCAIL_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -70,7 +70,13 @@ struct AttnParams {
     __nv_bfloat16* out;  // [B*q_rows_per_batch, ldo]; head h written at columns [h*128, h*128+128)
     int64_t ldo;
     int q_len;           // valid query rows per batch
-    int kv_len;          // valid key rows per batch
+    int kv_len;          // valid key rows per batch in the first key range (rows [kv_off, kv_off + kv_len) of the batch)
+    int kv_off;          // first key row of range 0 inside a batch
+    int kv_off1, kv_len1;  // optional second key range (kv_len1 == 0: none): context parallelism attends to "every shard but mine"
+    float* o32;          // optional: write the NORMALISED partial result as fp32 [rows, ldo32] instead of bf16 `out` ...
+    int64_t ldo32;
+    float2* state;       // ... together with (running max in log2 units, row sum) per (row, head): [rows * H], see attn_merge_kernel
+    int heads;
     int q_batch_rows;    // row stride between batches in the Q matrix / out matrix
     int kv_batch_rows;   // row stride between batches in the K/V matrices
     float scale_log2;    // softmax scale * log2(e)
@@ -248,8 +254,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d(q_smem + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_q, bar(B_QFULL), col + h * 64,
                                 qrow + t * ATT_BQ);
-            const int kvrow = batch * p.kv_batch_rows;
-            const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV;
+            const int kvbase = batch * p.kv_batch_rows;
+            const int n_kv0 = (p.kv_len + ATT_BKV - 1) / ATT_BKV;
+            const int n_kv = n_kv0 + (p.kv_len1 + ATT_BKV - 1) / ATT_BKV;
+            // tile j of the concatenated key ranges starts at this row (a range's last tile may run past its end: masked)
+            auto kv_row = [&](int j) { return kvbase + (j < n_kv0 ? p.kv_off + j * ATT_BKV : p.kv_off1 + (j - n_kv0) * ATT_BKV); };
             auto load_k = [&](int j) {
                 const int s = j % ATT_K_STAGES;
                 mbar_wait(bar(B_KEMPTY + s), ((j / ATT_K_STAGES) & 1) ^ 1, 10);
@@ -258,16 +267,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #endif
                 mbar_expect_tx(bar(B_KFULL + s), ATT_TILE_BYTES);
                 for (int h = 0; h < 2; ++h)
-                    tma_load_2d(k_smem + s * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_k, bar(B_KFULL + s), col + h * 64,
-                                kvrow + j * ATT_BKV);
+                    tma_load_2d(k_smem + s * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_k, bar(B_KFULL + s), col + h * 64, kv_row(j));
             };
             auto load_v = [&](int j) {
                 const int s = j % ATT_V_STAGES;
                 mbar_wait(bar(B_VEMPTY + s), ((j / ATT_V_STAGES) & 1) ^ 1, 11);
                 mbar_expect_tx(bar(B_VFULL + s), ATT_TILE_BYTES);
                 for (int h = 0; h < 2; ++h)
-                    tma_load_2d(v_smem + s * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_v, bar(B_VFULL + s), col + h * 64,
-                                kvrow + j * ATT_BKV);
+                    tma_load_2d(v_smem + s * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmap_v, bar(B_VFULL + s), col + h * 64, kv_row(j));
             };
             // K runs one tile ahead of V (QK^T of tile j+1 is issued during the PV work of tile j)
             load_k(0);
@@ -281,7 +288,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // The whole warp runs the control flow (waits, descriptor arithmetic stay warp-uniform => uniform
         // datapath); only the tcgen05 instructions themselves are issued by the elected lane.
         const bool leader = elect_one_sync();
-        const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV;
+        const int n_kv = (p.kv_len + ATT_BKV - 1) / ATT_BKV + (p.kv_len1 + ATT_BKV - 1) / ATT_BKV;
         constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
         const uint64_t q_desc0 = umma_desc_kmajor_sw128(q_smem), q_desc1 = umma_desc_kmajor_sw128(q_smem + ATT_TILE_BYTES);
@@ -378,32 +385,48 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t bar_p0 = bar(B_PFULL + tile * ATT_P_SPLIT);
         float m_run = -INFINITY;  // running max, already multiplied by scale_log2
         float l_run = 0.f;
-        const int n_full = p.kv_len / ATT_BKV;  // full tiles; an optional partial tile follows (peeled: no per-iteration branch)
-        for (int j = 0; j < n_full; ++j) {
+        int j = 0;  // tile counter over both key ranges (mbarrier parity, "first tile" test)
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const int len = r == 0 ? p.kv_len : p.kv_len1;
+            const int j_end = j + len / ATT_BKV;  // full tiles of this range; an optional partial tile follows (peeled)
+            for (; j < j_end; ++j) {
 #ifdef SCAIL_ATTN_EXPERIMENTS
-            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
+                const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
 #endif
-            SCAIL_ATTN_TRACE(j * 8 + 4);
-            mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
-            SCAIL_ATTN_TRACE(j * 8 + 5);
-            tc_fence_after();
+                SCAIL_ATTN_TRACE(j * 8 + 4);
+#ifdef SCAIL_ATT_ONE_POLLER
+                if (sub == 0) mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);  // one polling warp per Q tile ...
+                named_bar_sync(9 + tile, 128);                                    // ... the other three park on a hardware barrier
+#else
+                mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
+#endif
+                SCAIL_ATTN_TRACE(j * 8 + 5);
+                tc_fence_after();
 #ifdef SCAIL_ATTN_EXPERIMENTS
-            if (p.debug == 1 || p.debug >= 5) {  // pipeline only: no TMEM reads, no math
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    for (int g = 0; g < ATT_P_SPLIT; ++g) mbar_arrive(bar_p0 + 8u * g);
-                l_run = 1.f;
-                continue;
+                if (p.debug == 1 || p.debug >= 5) {  // pipeline only: no TMEM reads, no math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int g = 0; g < ATT_P_SPLIT; ++g) mbar_arrive(bar_p0 + 8u * g);
+                    l_run = 1.f;
+                    continue;
+                }
+#endif
+                softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, ATT_BKV, j, m_run, l_run, bar_p0);
+                SCAIL_ATTN_TRACE(j * 8 + 6);
             }
+            if (len % ATT_BKV) {  // partial last tile of the range: masked instantiation
+#ifdef SCAIL_ATT_ONE_POLLER
+                if (sub == 0) mbar_wait(bar(B_SFULL + tile), j & 1, 32 + tile);
+                named_bar_sync(9 + tile, 128);
+#else
+                mbar_wait(bar(B_SFULL + tile), j & 1, 32 + tile);
 #endif
-            softmax_tile<false>(s_tmem, o_tmem, p.scale_log2, ATT_BKV, j, m_run, l_run, bar_p0);
-            SCAIL_ATTN_TRACE(j * 8 + 6);
-        }
-        if (n_full * ATT_BKV < p.kv_len) {  // partial last KV tile: masked instantiation
-            mbar_wait(bar(B_SFULL + tile), n_full & 1, 32 + tile);
-            tc_fence_after();
-            softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, p.kv_len - n_full * ATT_BKV, n_full, m_run, l_run, bar_p0);
+                tc_fence_after();
+                softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, len % ATT_BKV, j, m_run, l_run, bar_p0);
+                ++j;
+            }
         }
         // ---- epilogue: O / l -> bf16 -> global ----
         mbar_wait(bar(B_OFULL + tile), 0, 40 + tile);
@@ -411,12 +434,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int qi = q0 + tile * ATT_BQ + sub * 32 + lane;
         const bool row_ok = qi < p.q_len;
         const float inv_l = 1.0f / l_run;
-        __nv_bfloat16* orow = p.out + (static_cast<int64_t>(batch) * p.q_batch_rows + qi) * p.ldo + head * ATT_D;
+        const int64_t grow = static_cast<int64_t>(batch) * p.q_batch_rows + qi;
+        __nv_bfloat16* orow = p.out + grow * p.ldo + head * ATT_D;
+        if (p.o32 != nullptr && row_ok) p.state[grow * p.heads + head] = make_float2(m_run, l_run);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
             tmem_ld_32x32(o_tmem + c * 32, o);
             tmem_ld_wait();
+            if (p.o32 != nullptr) {  // partial result over a subset of the keys: fp32, merged later (attn_merge_kernel)
+                if (row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(p.o32 + grow * p.ldo32 + head * ATT_D + c * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        dst[g] = make_float4(__uint_as_float(o[4 * g]) * inv_l, __uint_as_float(o[4 * g + 1]) * inv_l,
+                                             __uint_as_float(o[4 * g + 2]) * inv_l, __uint_as_float(o[4 * g + 3]) * inv_l);
+                }
+                continue;
+            }
             if (row_ok) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -451,6 +486,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, 512);
     }
+}
+
+// Combine two partial attention results over disjoint key sets (context parallelism: local shard first, remote shards once
+// the all-gather has landed).  Each partial is normalised by its own row sum l and carries (m, l) with m in log2 units:
+//   out = (w_a O_a + w_b O_b) / (w_a + w_b),  w_x = l_x 2^(m_x - max(m_a, m_b)).   One warp per (row, head).
+__global__ void __launch_bounds__(256) attn_merge_kernel(const float* __restrict__ oa, const float2* __restrict__ sa,
+                                                         const float* __restrict__ ob, const float2* __restrict__ sb,
+                                                         __nv_bfloat16* __restrict__ out, int64_t ld32, int64_t ldo, int64_t rows,
+                                                         int heads) {
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;  // (row, head)
+    if (item >= rows * heads) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = item / heads;
+    const int head = static_cast<int>(item - row * heads);
+    const float2 a = sa[item], b = sb[item];
+    const float m = fmaxf(a.x, b.x);
+    const float wa = a.y * fast_exp2(a.x - m), wb = b.y * fast_exp2(b.x - m);
+    const float inv = 1.0f / (wa + wb);
+    const float ca = wa * inv, cb = wb * inv;
+    const float4 va = *reinterpret_cast<const float4*>(oa + row * ld32 + head * ATT_D + lane * 4);
+    const float4 vb = *reinterpret_cast<const float4*>(ob + row * ld32 + head * ATT_D + lane * 4);
+    uint2 o;
+    o.x = pack_bf16(ca * va.x + cb * vb.x, ca * va.y + cb * vb.y);
+    o.y = pack_bf16(ca * va.z + cb * vb.z, ca * va.w + cb * vb.w);
+    *reinterpret_cast<uint2*>(out + row * ldo + head * ATT_D + lane * 4) = o;
 }
 
 }  // namespace scail

@@ -103,6 +103,42 @@ def attention(q, k, v, out, B, H, q_len, kv_len, q_batch_rows=None, kv_batch_row
     return out
 
 
+def attention_partial(q, k, v, o32, state, B, H, q_len, ranges, q_batch_rows=None, kv_batch_rows=None, scale=None):
+    """Attention of q over the key rows `ranges` = [(off0, len0)] or [(off0, len0), (off1, len1)] of every batch (offsets inside a
+    batch of kv_batch_rows rows).  o32: fp32 [rows, H*128] (normalised partial result), state: fp32 [rows, H, 2] = (max, sum)."""
+    for t in (q, k, v):
+        _req(t)
+        assert t.dim() == 2 and t.stride(1) == 1
+    _req(o32, torch.float32), _req(state, torch.float32)
+    assert o32.dim() == 2 and o32.stride(1) == 1 and state.is_contiguous() and state.numel() == o32.shape[0] * H * 2
+    (o0, l0) = ranges[0]
+    (o1, l1) = ranges[1] if len(ranges) > 1 else (0, 0)
+    q_batch_rows = q_len if q_batch_rows is None else q_batch_rows
+    scale = 1.0 / math.sqrt(128) if scale is None else scale
+    ev = None
+    if ATTN_EVENTS is not None and l0 + l1 > 1024:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.check(_lib.lib().scail_attention_partial(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o32),
+                                                  o32.stride(0), _ptr(state), B, H, q_len, o0, l0, o1, l1, q_batch_rows,
+                                                  kv_batch_rows, q.shape[0], k.shape[0], scale, _stream()), "scail_attention_partial")
+    if ev is not None:
+        ev[1].record()
+        ATTN_EVENTS.append(ev)
+    _count()
+
+
+def attention_merge(o32_a, state_a, o32_b, state_b, out, H):
+    """out (bf16 [rows, H*128]) = merge of two partial attention results over disjoint key sets (see attention_partial)."""
+    _req(out)
+    rows = out.shape[0]
+    assert o32_a.shape == o32_b.shape and o32_a.stride(0) == o32_b.stride(0) and out.stride(1) == 1
+    _lib.check(_lib.lib().scail_attention_merge(_ptr(o32_a), _ptr(state_a), _ptr(o32_b), _ptr(state_b), _ptr(out), o32_a.stride(0),
+                                                out.stride(0), rows, H, _stream()), "scail_attention_merge")
+    _count()
+    return out
+
+
 def adaln_modulation(emb, param, out=None):
     _req(emb), _req(param)
     B, n = emb.shape

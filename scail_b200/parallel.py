@@ -22,6 +22,7 @@ class ContextParallel:
         self._kv = {}
         self._q = {}
         self._streams = {}
+        self.local_first = self.size > 1  # overlap the K/V all-gather with attention over the local shard
 
     def branch_streams(self, n, device):
         key = (n, str(device))
@@ -106,11 +107,33 @@ class ContextParallel:
         q = self._q[qkey]
         ops.gemm(h2, w[:d], bias[:d], out=q)  # overlaps the all-gathers
         ops.rmsnorm_rope(q, n_local, d, [(0, wq)], cos_l, sin_l, eps=eps)
+        k2, v2 = kbuf.view(B * P * n_local, d), vbuf.view(B * P * n_local, d)
+        if not self.local_first:
+            for wk_ in works:
+                wk_.wait()
+            ops.attention(q, k2, v2, ctx, B, H, n_local, P * n_local, q_batch_rows=n_local, kv_batch_rows=P * n_local)
+            return ctx
+        # Local shard first ("attention over the local K/V shard starts immediately; remote shards consumed as
+        # they arrive"): the partial over this rank's own keys runs while the all-gathers are in flight, the partial over all
+        # other shards once they have landed; the two are merged with their softmax statistics (fp32 partials: the only
+        # difference to one pass over all keys is fp32 summation order).
+        o_a, st_a, o_b, st_b = self._partials(B * n_local, d, H, dev)
+        r = self.rank
+        ops.attention_partial(q, k2, v2, o_a, st_a, B, H, n_local, [(r * n_local, n_local)], q_batch_rows=n_local,
+                              kv_batch_rows=P * n_local)
         for wk_ in works:
             wk_.wait()
-        ops.attention(q, kbuf.view(B * P * n_local, d), vbuf.view(B * P * n_local, d), ctx, B, H, n_local, P * n_local,
-                      q_batch_rows=n_local, kv_batch_rows=P * n_local)
+        remote = [(o, l) for (o, l) in ((0, r * n_local), ((r + 1) * n_local, (P - 1 - r) * n_local)) if l > 0]
+        ops.attention_partial(q, k2, v2, o_b, st_b, B, H, n_local, remote, q_batch_rows=n_local, kv_batch_rows=P * n_local)
+        ops.attention_merge(o_a, st_a, o_b, st_b, ctx, H)
         return ctx
+
+    def _partials(self, rows, d, H, dev):
+        key = ("partials", rows, d, H, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        if key not in self._q:
+            self._q[key] = (torch.empty(rows, d, device=dev, dtype=torch.float32), torch.empty(rows, H, 2, device=dev, dtype=torch.float32),
+                            torch.empty(rows, d, device=dev, dtype=torch.float32), torch.empty(rows, H, 2, device=dev, dtype=torch.float32))
+        return self._q[key]
 
 
 class HybridParallel:

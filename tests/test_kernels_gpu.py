@@ -173,6 +173,39 @@ def test_attention_fused_qkv_layout_and_accumulate():
     assert rel(out.view(B, n, D), ref2) < 8e-3
 
 
+@pytest.mark.parametrize("P,n_local,rank", [(4, 200, 1), (2, 384, 0), (4, 328, 3), (8, 100, 5)])
+def test_attention_partial_and_merge(P, n_local, rank):
+    """Context-parallel split: partial over the local key shard + partial over every other shard (two row ranges, not
+    tile-aligned), merged with their softmax statistics, equals attention over all keys."""
+    from oracle import dit_oracle as O
+    from scail_b200 import ops
+    B, H = 2, 2
+    D = H * 128
+    nkv = P * n_local
+    q, k, v = rnd(B * n_local, D, seed=1), rnd(B * nkv, D, seed=2), rnd(B * nkv, D, seed=3)
+    full = torch.zeros(B * n_local, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, full, B, H, n_local, nkv)
+    oa = torch.empty(B * n_local, D, device="cuda", dtype=torch.float32)
+    ob = torch.empty_like(oa)
+    sa = torch.empty(B * n_local, H, 2, device="cuda", dtype=torch.float32)
+    sb = torch.empty_like(sa)
+    ops.attention_partial(q, k, v, oa, sa, B, H, n_local, [(rank * n_local, n_local)], kv_batch_rows=nkv)
+    remote = [(o, l) for (o, l) in ((0, rank * n_local), ((rank + 1) * n_local, (P - 1 - rank) * n_local)) if l > 0]
+    ops.attention_partial(q, k, v, ob, sb, B, H, n_local, remote, kv_batch_rows=nkv)
+    out = torch.zeros_like(full)
+    ops.attention_merge(oa, sa, ob, sb, out, H)
+    torch.cuda.synchronize()
+    ref = O.merge_heads(O.sdpa(O.heads(q.float().view(B, n_local, D), H), O.heads(k.float().view(B, nkv, D), H),
+                               O.heads(v.float().view(B, nkv, D), H)))
+    assert rel(out.view(B, n_local, D), ref) < 6e-3
+    assert rel(out, full) < 3e-3  # vs the single pass: only rounding-order differences
+    # the local partial alone is attention over the local shard
+    kl = k.view(B, nkv, D)[:, rank * n_local:(rank + 1) * n_local].float()
+    vl = v.view(B, nkv, D)[:, rank * n_local:(rank + 1) * n_local].float()
+    ref_l = O.merge_heads(O.sdpa(O.heads(q.float().view(B, n_local, D), H), O.heads(kl, H), O.heads(vl, H)))
+    assert rel(oa.view(B, n_local, D), ref_l) < 6e-3
+
+
 def test_attention_large_scores_rescale_path():
     """Scores with a growing row max force the lazy O-rescale branch (max grows by > 2^8 between tiles)."""
     from oracle import dit_oracle as O
