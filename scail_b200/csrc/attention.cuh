@@ -395,12 +395,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64 && warp == 0 && lane == 0;
 #endif
                 SCAIL_ATTN_TRACE(j * 8 + 4);
-#ifdef SCAIL_ATT_ONE_POLLER
-                if (sub == 0) mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);  // one polling warp per Q tile ...
-                named_bar_sync(9 + tile, 128);                                    // ... the other three park on a hardware barrier
-#else
                 mbar_wait(bar(B_SFULL + tile), j & 1, 30 + tile);
-#endif
                 SCAIL_ATTN_TRACE(j * 8 + 5);
                 tc_fence_after();
 #ifdef SCAIL_ATTN_EXPERIMENTS
@@ -417,12 +412,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 SCAIL_ATTN_TRACE(j * 8 + 6);
             }
             if (len % ATT_BKV) {  // partial last tile of the range: masked instantiation
-#ifdef SCAIL_ATT_ONE_POLLER
-                if (sub == 0) mbar_wait(bar(B_SFULL + tile), j & 1, 32 + tile);
-                named_bar_sync(9 + tile, 128);
-#else
                 mbar_wait(bar(B_SFULL + tile), j & 1, 32 + tile);
-#endif
                 tc_fence_after();
                 softmax_tile<true>(s_tmem, o_tmem, p.scale_log2, len % ATT_BKV, j, m_run, l_run, bar_p0);
                 ++j;
