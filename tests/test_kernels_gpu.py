@@ -276,6 +276,11 @@ def test_error_paths_return_codes_not_crashes():
         ops.gemm(a, w, epilogue=17)
     with pytest.raises(RuntimeError, match="gate/residual required"):
         ops.gemm(a, w, epilogue=ops.EPI_BIAS_GATE_RES)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):  # the epilogue uses 16-byte accesses
+        ops.gemm(a, w, rnd(w.shape[0] + 8)[4:4 + w.shape[0]])      # bias view at an 8-byte offset
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        big = torch.empty(a.shape[0], w.shape[0] + 4, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, out=big[:, :w.shape[0]])                    # bf16 output with ldc % 8 == 4
     x = rnd(2, 4, 388)
     with pytest.raises(RuntimeError, match="multiple of 8"):
         ops.ln_modulate(x)
