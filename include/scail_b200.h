@@ -93,6 +93,20 @@ int scail_attention_partial(const void* Q, int64_t ldq, const void* K, int64_t l
 int scail_attention_merge(const float* o32_a, const void* state_a, const float* o32_b, const void* state_b, void* out,
                           int64_t ldo32, int64_t ldo, int64_t rows, int64_t H, scail_stream_t stream);
 
+/* Context-parallel collective (the path's one exchange step: the per-block K/V all-gather over the sequence-parallel group,
+ * replacing the 12 all_to_all_single calls per block of sat/mpu/ulysses_attn_layer.py:41-110 / sat/mpu/all_to_all.py:15-109).
+ * NCCL is bound at run time (dlopen of libnccl.so.2; `nccl_path` may name a specific file, NULL = the one already loaded by the
+ * process).  scail_cp_unique_id: 128-byte id created on one rank and shipped to the others by the host (e.g. a
+ * torch.distributed broadcast).  scail_cp_init: join with the CURRENT CUDA device, returns a handle >= 0.
+ * scail_cp_allgather: recv = nranks consecutive slots of bytes_per_rank bytes, rank r's data in slot r (send may alias it);
+ * enqueued on the group's own high-priority stream after everything already on compute_stream (event hand-off), returns at
+ * once.  scail_cp_wait: compute_stream waits (device-side) for the group's outstanding collectives. */
+int scail_cp_unique_id(void* out128, const char* nccl_path);
+int scail_cp_init(const void* unique_id128, int rank, int nranks, const char* nccl_path);
+int scail_cp_allgather(int handle, const void* send, void* recv, int64_t bytes_per_rank, scail_stream_t compute_stream);
+int scail_cp_wait(int handle, scail_stream_t compute_stream);
+int scail_cp_destroy(int handle);
+
 /* mod[b, i] = emb[b, i] + param[i]  (shared-AdaLN modulation vectors, dit_video_crossattn_sc_xc.py:1025-1028, 823) */
 int scail_adaln_modulation(const void* emb, const void* param, void* out, int64_t B, int64_t n, scail_stream_t stream);
 int scail_silu(const void* x, void* out, int64_t n, scail_stream_t stream);

@@ -32,6 +32,11 @@ SIGNATURES = {
     "scail_attention_partial": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_f, c_p],
     "scail_attention_merge": [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p],
+    "scail_cp_unique_id": [c_p, ctypes.c_char_p],
+    "scail_cp_init": [c_p, c_int, c_int, ctypes.c_char_p],
+    "scail_cp_allgather": [c_int, c_p, c_p, c_i64, c_p],
+    "scail_cp_wait": [c_int, c_p],
+    "scail_cp_destroy": [c_int],
     "scail_adaln_modulation": [c_p, c_p, c_p, c_i64, c_i64, c_p],
     "scail_silu": [c_p, c_p, c_i64, c_p],
     "scail_timestep_embedding": [c_p, c_p, c_i64, c_i64, c_p],
@@ -69,7 +74,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     extra = os.environ.get("SCAIL_NVCC_EXTRA", "").split()  # e.g. -DSCAIL_ATTN_EXPERIMENTS for scripts/trace_attn.py
-    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", LIB_PATH, os.path.join(CSRC, "api.cu"), "-lcudart"]
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", LIB_PATH, os.path.join(CSRC, "api.cu"), "-lcudart", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -3,6 +3,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -596,6 +598,134 @@ int scail_softmax_rows(const float* s, void* p, int64_t rows, int64_t cols, floa
     scail::softmax_rows_kernel<<<blocks_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         s, static_cast<__nv_bfloat16*>(p), (int)rows, (int)cols, scale);
     SCAIL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Context-parallel collective (SURVEY.md 8b "collective"): the one exchange step of the path -- the per-block K/V all-gather
+// over the sequence-parallel group -- behind the C ABI, on a library-owned communication stream with event hand-off.
+// NCCL is bound at run time (dlopen of the libnccl.so.2 the process already uses, i.e. PyTorch's): no link-time dependency,
+// and nothing here exists without it (no fallback: scail_cp_init fails loudly).
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct UniqueId { char b[128]; };
+typedef int (*CommInitRankFn)(void**, int, UniqueId, int);
+NcclApi g_nccl;
+CommInitRankFn g_nccl_init = nullptr;
+
+int load_nccl(const char* path) {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {path, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(-4, "cp: cannot dlopen libnccl (%s)", dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+    g_nccl_init = reinterpret_cast<CommInitRankFn>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+    g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(g_nccl.lib, "ncclAllGather"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl_init || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+        g_nccl.lib = nullptr;
+        return fail(-4, "cp: libnccl lacks a required symbol");
+    }
+    return 0;
+}
+
+struct CpGroup {
+    void* comm = nullptr;
+    int rank = 0, nranks = 0;
+    cudaStream_t stream = nullptr;   // library-owned communication stream
+    cudaEvent_t ready = nullptr;     // recorded on the caller's stream before a collective
+    cudaEvent_t done = nullptr;      // recorded on the communication stream after the last collective
+};
+constexpr int MAX_CP_GROUPS = 16;
+CpGroup g_cp[MAX_CP_GROUPS];
+
+#define SCAIL_CHECK_NCCL(expr)                                                                                       \
+    do {                                                                                                             \
+        int _r = (expr);                                                                                             \
+        if (_r != 0) return fail(-4, "%s: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error"); \
+    } while (0)
+
+}  // namespace
+
+/* 128-byte NCCL unique id for a new group (call on one rank, ship to the others with any host-side channel). */
+int scail_cp_unique_id(void* out128, const char* nccl_path) {
+    SCAIL_REQUIRE(out128, "cp_unique_id: null");
+    int rc;
+    if ((rc = load_nccl(nccl_path))) return rc;
+    SCAIL_CHECK_NCCL(g_nccl.GetUniqueId(out128));
+    return 0;
+}
+
+/* Join the group; the current CUDA device is the rank's GPU.  Returns a handle >= 0. */
+int scail_cp_init(const void* unique_id128, int rank, int nranks, const char* nccl_path) {
+    SCAIL_REQUIRE(unique_id128 && nranks >= 1 && rank >= 0 && rank < nranks, "cp_init: bad args");
+    int rc;
+    if ((rc = load_nccl(nccl_path))) return rc;
+    int h = -1;
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        for (int i = 0; i < MAX_CP_GROUPS; ++i)
+            if (!g_cp[i].comm) { h = i; break; }
+    }
+    SCAIL_REQUIRE(h >= 0, "cp_init: too many groups");
+    UniqueId id;
+    memcpy(id.b, unique_id128, 128);
+    CpGroup g;
+    g.rank = rank; g.nranks = nranks;
+    SCAIL_CHECK_NCCL(g_nccl_init(&g.comm, nranks, id, rank));
+    int lo = 0, hi = 0;
+    SCAIL_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SCAIL_CHECK_CUDA(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, hi));  // highest priority: gathers first
+    SCAIL_CHECK_CUDA(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+    SCAIL_CHECK_CUDA(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    g_cp[h] = g;
+    return h;
+}
+
+/* In-place-capable all-gather of `bytes_per_rank` bytes: recv holds nranks consecutive slots, rank r's slot is
+ * recv + r * bytes_per_rank (send may alias this rank's slot).  Ordered after everything already enqueued on
+ * `compute_stream`; runs on the group's own stream; returns immediately (scail_cp_wait joins). */
+int scail_cp_allgather(int handle, const void* send, void* recv, int64_t bytes_per_rank, scail_stream_t compute_stream) {
+    SCAIL_REQUIRE(handle >= 0 && handle < MAX_CP_GROUPS && g_cp[handle].comm, "cp_allgather: bad handle");
+    SCAIL_REQUIRE(send && recv && bytes_per_rank > 0, "cp_allgather: bad args");
+    CpGroup& g = g_cp[handle];
+    SCAIL_CHECK_CUDA(cudaEventRecord(g.ready, static_cast<cudaStream_t>(compute_stream)));
+    SCAIL_CHECK_CUDA(cudaStreamWaitEvent(g.stream, g.ready, 0));
+    SCAIL_CHECK_NCCL(g_nccl.AllGather(send, recv, static_cast<size_t>(bytes_per_rank), /*ncclInt8*/ 0, g.comm, g.stream));
+    SCAIL_CHECK_CUDA(cudaEventRecord(g.done, g.stream));
+    return 0;
+}
+
+/* Make `compute_stream` wait for every collective enqueued on the group so far (device-side, no host sync). */
+int scail_cp_wait(int handle, scail_stream_t compute_stream) {
+    SCAIL_REQUIRE(handle >= 0 && handle < MAX_CP_GROUPS && g_cp[handle].comm, "cp_wait: bad handle");
+    SCAIL_CHECK_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(compute_stream), g_cp[handle].done, 0));
+    return 0;
+}
+
+int scail_cp_destroy(int handle) {
+    SCAIL_REQUIRE(handle >= 0 && handle < MAX_CP_GROUPS && g_cp[handle].comm, "cp_destroy: bad handle");
+    CpGroup g = g_cp[handle];
+    cudaStreamSynchronize(g.stream);
+    g_nccl.CommDestroy(g.comm);
+    cudaEventDestroy(g.ready);
+    cudaEventDestroy(g.done);
+    cudaStreamDestroy(g.stream);
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    g_cp[handle] = CpGroup();
     return 0;
 }
 

@@ -8,17 +8,40 @@ same softmax over the same key set, so parity is checked against the single-GPU 
 The all-gather is issued asynchronously (NCCL stream) right after the K/V projection so that the Q projection
 and its RMSNorm+RoPE overlap the transfer.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 
 
+class _NativeWork:
+    """Handle of collectives enqueued through libscail_b200's scail_cp_allgather: wait() makes the CURRENT stream wait (device
+    side) for the group's communication stream, like torch.distributed's Work.wait() does for NCCL work."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def wait(self):
+        from . import _lib
+        _lib.check(_lib.lib().scail_cp_wait(self.handle, torch.cuda.current_stream().cuda_stream), "scail_cp_wait")
+
+
 class ContextParallel:
-    def __init__(self, group=None):
+    def __init__(self, group=None, native=None):
+        """native=True routes the K/V all-gather through the library's own NCCL communicator and communication stream
+        (scail_cp_* in the C ABI: SURVEY 8b "collective"); False uses torch.distributed.all_gather_into_tensor.  Default: the
+        SCAIL_CP_NATIVE environment variable (off unless set to 1)."""
         self.group = group if group is not None else dist.group.WORLD
         self.size = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        self._handle = None
+        if native is None:
+            native = os.environ.get("SCAIL_CP_NATIVE", "0") == "1"
+        if native and self.size > 1 and torch.cuda.is_available() and dist.get_backend(self.group) == "nccl":
+            self._init_native()
         self._kv = {}
         self._q = {}
         self._streams = {}
@@ -28,6 +51,22 @@ class ContextParallel:
         # the exposed part of the gather that the Q projection does not already cover; outputs are then no longer bit-identical
         # to one GPU (cp_check_rel 1.8e-2 on the x4-amplified guided velocity).  Kept for larger CP degrees / slower links.
         self.local_first = False
+
+    def _init_native(self):
+        from . import _lib
+        h = _lib.lib()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_char * 128)()
+            _lib.check(h.scail_cp_unique_id(ctypes.cast(buf, ctypes.c_void_p), None), "scail_cp_unique_id")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()  # the id travels over the existing torch.distributed group (host-side plumbing)
+        dist.broadcast(uid, src=dist.get_global_rank(self.group, 0), group=self.group)
+        raw = bytes(uid.cpu().tolist())
+        rc = h.scail_cp_init(ctypes.cast(ctypes.create_string_buffer(raw, 128), ctypes.c_void_p), self.rank, self.size, None)
+        if rc < 0:
+            _lib.check(rc, "scail_cp_init")
+        self._handle = rc
 
     def branch_streams(self, n, device):
         key = (n, str(device))
@@ -70,6 +109,14 @@ class ContextParallel:
     def gather_kv(self, kvbuf, async_op=True):
         """In-place all-gather per batch element: rank r's slot kvbuf[b, r] is sent, kvbuf[b] receives all."""
         B, P, n, w = kvbuf.shape
+        if self._handle is not None:
+            from . import _lib
+            st = torch.cuda.current_stream(kvbuf.device).cuda_stream
+            nbytes = n * w * kvbuf.element_size()
+            for b in range(B):
+                _lib.check(_lib.lib().scail_cp_allgather(self._handle, kvbuf[b, self.rank].data_ptr(), kvbuf[b].data_ptr(), nbytes,
+                                                         st), "scail_cp_allgather")
+            return [_NativeWork(self._handle)]
         works = []
         for b in range(B):
             works.append(dist.all_gather_into_tensor(kvbuf[b].view(P * n, w), kvbuf[b, self.rank], group=self.group,

@@ -39,6 +39,12 @@ def _worker(rank, world, port, q):
             single = m(x, **kw).float()
             m.mixins["adaln_layer"].cp = ContextParallel()
             multi = m(x, **kw).float()
+            # ---- the same through the library's own collective (scail_cp_* in the C ABI: NCCL communicator + communication stream
+            # owned by libscail_b200.so) instead of torch.distributed.all_gather_into_tensor: must not change a bit ----
+            m.mixins["adaln_layer"].cp = ContextParallel(native=True)
+            assert m.mixins["adaln_layer"].cp._handle is not None
+            native = m(x, **kw).float()
+            assert torch.equal(native, multi), float((native - multi).abs().max())
             # ---- engine-style sequence parallelism (diffusion_video.py:495-552): every rank gets its H- (or W-) chunk of the
             # latents / ref / pose, passes chunk_dim, and returns its chunk of the output; the engine gathers on chunk_dim ----
             rels = []
