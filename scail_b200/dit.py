@@ -271,8 +271,11 @@ class FinalLayerMixin(BaseMixin):
         _need_cuda(x)
         B, N, d = x.shape
         n_ref, n_seq = kwargs["ref_length"], kwargs["seq_length"]
-        mod = ops.adaln_modulation(emb.repeat(1, 2).contiguous(), self.adaLN_modulation.view(-1)).view(B, 2, d)
-        xin = ops.ln_modulate(x.contiguous(), shift=mod[:, 0], scale=mod[:, 1], eps=self.layernorm_epsilon,
+        # shift, scale = (emb + adaLN_modulation[0, {0, 1}])  (:823): two launches of the library kernel, no eager torch op
+        emb = emb.contiguous()
+        shift = ops.adaln_modulation(emb, self.adaLN_modulation[0, 0])
+        scale = ops.adaln_modulation(emb, self.adaLN_modulation[0, 1])
+        xin = ops.ln_modulate(x.contiguous(), shift=shift, scale=scale, eps=self.layernorm_epsilon,
                               rows_out=n_seq, row_offset=n_ref)
         lin = ops.gemm(xin.view(B * n_seq, d), self.linear.weight, self.linear.bias)
         return ops.unpatchify(lin, B, kwargs["rope_T"], kwargs["rope_H"], kwargs["rope_W"])
