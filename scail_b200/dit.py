@@ -319,6 +319,12 @@ class AdaLNMixin(BaseMixin):
 
     # -- hooks ---------------------------------------------------------------------------------
     def layer_forward(self, hidden_states, mask, *args, **kwargs):
+        """One DiT block (:1009-1051).  IN-PLACE contract: when `hidden_states` is a contiguous bf16 tensor (what
+        word_embedding_forward / the previous layer_forward return) the residual stream is updated in that very buffer by the
+        fused `x + gate * (acc + bias)` GEMM epilogues and the same tensor is returned — the reference's out-of-place
+        `hidden_states = hidden_states + ...` semantics are preserved for its caller (BaseTransformer.forward rebinds the name,
+        sat/model/transformer.py:712-722), but a caller that keeps its own reference to the input sees it change.  Any other
+        dtype / layout is first copied to a fresh bf16 buffer."""
         _need_cuda(hidden_states)
         l = int(kwargs["layer_id"])
         layer = self.transformer.layers[l]
