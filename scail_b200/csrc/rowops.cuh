@@ -44,8 +44,30 @@ struct LnModParams {
     float eps;
 };
 
+// bf16x2 word -> packed f32x2 (two ALU ops), and the packed math below halve the instruction count of the row kernels, which
+// are otherwise ALU-bound on bf16 unpacking before they are HBM-bound.
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t w) {
+    return pack_f32x2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
+    float lo, hi;
+    unpack_f32x2(v, lo, hi);
+    return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ float hsum_f32x2(uint64_t v) {
+    float lo, hi;
+    unpack_f32x2(v, lo, hi);
+    return lo + hi;
+}
+
 // LayerNorm (+optional affine) (+optional AdaLN modulate x*(1+scale)+shift).
 // Restates F.layer_norm + modulate (dit_video_crossattn_sc_xc.py:760-761, :1031-1032, :1045-1046, :825).
+// The row is unpacked to fp32 pairs once and stays in registers (4 x ROW_MAXV packed f32x2 per thread) for all three passes.
 __global__ void __launch_bounds__(ROW_THREADS) ln_modulate_kernel(const LnModParams p) {
     __shared__ float red[4];
     const int row = blockIdx.x;
@@ -54,76 +76,65 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_modulate_kernel(const LnModPar
     const int64_t in_row = static_cast<int64_t>(b) * p.in_batch_rows + p.in_row_offset + r;
     const uint4* xin = reinterpret_cast<const uint4*>(p.x + in_row * p.D);
     const int nvec = p.D >> 3;  // 16-byte vectors in the row
-    uint4 v[ROW_MAXV];
-    float sum = 0.f;
+    uint64_t x[ROW_MAXV][4];
+    uint64_t acc = 0ull;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
         const int i = j * ROW_THREADS + threadIdx.x;
         if (i < nvec) {
-            v[j] = xin[i];
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            const uint4 v = xin[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float2 f = unpack_bf16(w[k]);
-                sum += f.x + f.y;
+                x[j][k] = bf16x2_to_f32x2(w[k]);
+                acc = add_f32x2(acc, x[j][k]);
             }
         }
     }
-    const float mean = row_block_sum(sum, red) / p.D;
-    float sq = 0.f;
+    const float mean = row_block_sum(hsum_f32x2(acc), red) / p.D;
+    const uint64_t nmean2 = pack_f32x2(-mean, -mean);
+    acc = 0ull;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
         if (j * ROW_THREADS + threadIdx.x < nvec) {
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float2 f = unpack_bf16(w[k]);
-                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+                x[j][k] = add_f32x2(x[j][k], nmean2);  // centred
+                acc = fma_f32x2(x[j][k], x[j][k], acc);
             }
         }
     }
-    const float rstd = rsqrtf(row_block_sum(sq, red) / p.D + p.eps);
+    const float rstd = rsqrtf(row_block_sum(hsum_f32x2(acc), red) / p.D + p.eps);
+    const uint64_t rstd2 = pack_f32x2(rstd, rstd), one2 = pack_f32x2(1.0f, 1.0f);
     uint4* o = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(row) * p.D);
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
         const int i = j * ROW_THREADS + threadIdx.x;
         if (i < nvec) {
             const int col = i * 8;
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-            float f[8];
+            uint64_t y[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float2 t = unpack_bf16(w[k]);
-                f[2 * k] = (t.x - mean) * rstd;
-                f[2 * k + 1] = (t.y - mean) * rstd;
-            }
+            for (int k = 0; k < 4; ++k) y[k] = mul_f32x2(x[j][k], rstd2);
             if (p.gamma) {
-                uint4 g = *reinterpret_cast<const uint4*>(p.gamma + col);
-                uint4 bb = *reinterpret_cast<const uint4*>(p.beta + col);
+                const uint4 g = *reinterpret_cast<const uint4*>(p.gamma + col);
+                const uint4 bb = *reinterpret_cast<const uint4*>(p.beta + col);
                 const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float2 g2 = unpack_bf16(gw[k]), b2 = unpack_bf16(bw[k]);
-                    f[2 * k] = f[2 * k] * g2.x + b2.x;
-                    f[2 * k + 1] = f[2 * k + 1] * g2.y + b2.y;
-                }
+                for (int k = 0; k < 4; ++k) y[k] = fma_f32x2(y[k], bf16x2_to_f32x2(gw[k]), bf16x2_to_f32x2(bw[k]));
             }
             if (p.scale) {
-                uint4 s = *reinterpret_cast<const uint4*>(p.scale + b * p.mod_stride + col);
-                uint4 h = *reinterpret_cast<const uint4*>(p.shift + b * p.mod_stride + col);
-                const uint32_t sw[4] = {s.x, s.y, s.z, s.w}, hw[4] = {h.x, h.y, h.z, h.w};
+                const uint4 sc = *reinterpret_cast<const uint4*>(p.scale + b * p.mod_stride + col);
+                const uint4 sh = *reinterpret_cast<const uint4*>(p.shift + b * p.mod_stride + col);
+                const uint32_t sw[4] = {sc.x, sc.y, sc.z, sc.w}, hw[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float2 s2 = unpack_bf16(sw[k]), h2 = unpack_bf16(hw[k]);
-                    f[2 * k] = f[2 * k] * (1.0f + s2.x) + h2.x;
-                    f[2 * k + 1] = f[2 * k + 1] * (1.0f + s2.y) + h2.y;
-                }
+                for (int k = 0; k < 4; ++k)
+                    y[k] = fma_f32x2(y[k], add_f32x2(one2, bf16x2_to_f32x2(sw[k])), bf16x2_to_f32x2(hw[k]));
             }
             uint4 ov;
-            ov.x = pack_bf16(f[0], f[1]);
-            ov.y = pack_bf16(f[2], f[3]);
-            ov.z = pack_bf16(f[4], f[5]);
-            ov.w = pack_bf16(f[6], f[7]);
+            ov.x = f32x2_to_bf16x2(y[0]);
+            ov.y = f32x2_to_bf16x2(y[1]);
+            ov.z = f32x2_to_bf16x2(y[2]);
+            ov.w = f32x2_to_bf16x2(y[3]);
             o[i] = ov;
         }
     }
@@ -152,63 +163,55 @@ __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_rope_kernel(const RmsRope
     __nv_bfloat16* base = p.buf + static_cast<int64_t>(row) * p.ld + (slab ? p.col_offset[1] : p.col_offset[0]);
     uint4* xin = reinterpret_cast<uint4*>(base);
     const int nvec = p.D >> 3;
-    uint4 v[ROW_MAXV];
-    float sq = 0.f;
+    uint64_t x[ROW_MAXV][4];  // the row as packed fp32 pairs (pair = one interleaved RoPE pair)
+    uint64_t acc = 0ull;
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
         const int i = j * ROW_THREADS + threadIdx.x;
         if (i < nvec) {
-            v[j] = xin[i];
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            const uint4 v = xin[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float2 f = unpack_bf16(w[k]);
-                sq += f.x * f.x + f.y * f.y;
+                x[j][k] = bf16x2_to_f32x2(w[k]);
+                acc = fma_f32x2(x[j][k], x[j][k], acc);
             }
         }
     }
     // head_dim = 128 = 16 vectors and ROW_THREADS % 16 == 0: the rope column (col % 128) of a thread is (tid % 16) * 8
     // for every vector it owns, so one (cos, sin) octet per thread serves the whole row; fetched before the reduction
-    // so that its latency hides behind it
-    float4 ca, cb, sa, sb;
+    // so that its latency hides behind it.  out pair = (x1, x2) * (c0, c1) + (x2, x1) * (-s0, s1)   (:336-340)
+    uint64_t c2[4], s2[4];
     const bool rope = p.cos != nullptr;
     if (rope) {
         const int tok = row % p.rows_per_batch;
         const float4* c4 = reinterpret_cast<const float4*>(p.cos + static_cast<int64_t>(tok) * 128 + (threadIdx.x & 15) * 8);
         const float4* s4 = reinterpret_cast<const float4*>(p.sin + static_cast<int64_t>(tok) * 128 + (threadIdx.x & 15) * 8);
-        ca = c4[0]; cb = c4[1]; sa = s4[0]; sb = s4[1];
+        const float4 ca = c4[0], cb = c4[1], sa = s4[0], sb = s4[1];
+        c2[0] = pack_f32x2(ca.x, ca.y); c2[1] = pack_f32x2(ca.z, ca.w); c2[2] = pack_f32x2(cb.x, cb.y); c2[3] = pack_f32x2(cb.z, cb.w);
+        s2[0] = pack_f32x2(-sa.x, sa.y); s2[1] = pack_f32x2(-sa.z, sa.w); s2[2] = pack_f32x2(-sb.x, sb.y); s2[3] = pack_f32x2(-sb.z, sb.w);
     }
-    const float rstd = rsqrtf(row_block_sum(sq, red) / p.D + p.eps);
+    const float rstd = rsqrtf(row_block_sum(hsum_f32x2(acc), red) / p.D + p.eps);
+    const uint64_t rstd2 = pack_f32x2(rstd, rstd);
     const __nv_bfloat16* wgt = slab ? p.weight[1] : p.weight[0];  // (a dynamic index would spill the param arrays to local memory)
 #pragma unroll
     for (int j = 0; j < ROW_MAXV; ++j) {
         const int i = j * ROW_THREADS + threadIdx.x;
         if (i < nvec) {
-            uint4 g = *reinterpret_cast<const uint4*>(wgt + i * 8);
-            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, gw[4] = {g.x, g.y, g.z, g.w};
-            float f[8];
+            const uint4 g = *reinterpret_cast<const uint4*>(wgt + i * 8);
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+            uint32_t ow[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float2 t = unpack_bf16(w[k]), g2 = unpack_bf16(gw[k]);
-                f[2 * k] = g2.x * (t.x * rstd);
-                f[2 * k + 1] = g2.y * (t.y * rstd);
-            }
-            if (rope) {
-                const float cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                const float sn[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float x1 = f[2 * k], x2 = f[2 * k + 1];
-                    f[2 * k] = x1 * cs[2 * k] - x2 * sn[2 * k];
-                    f[2 * k + 1] = x2 * cs[2 * k + 1] + x1 * sn[2 * k + 1];
+                uint64_t y = mul_f32x2(bf16x2_to_f32x2(gw[k]), mul_f32x2(x[j][k], rstd2));  // g * (x * rstd), as the reference orders it
+                if (rope) {
+                    float y1, y2;
+                    unpack_f32x2(y, y1, y2);
+                    y = fma_f32x2(pack_f32x2(y2, y1), s2[k], mul_f32x2(y, c2[k]));
                 }
+                ow[k] = f32x2_to_bf16x2(y);
             }
-            uint4 ov;
-            ov.x = pack_bf16(f[0], f[1]);
-            ov.y = pack_bf16(f[2], f[3]);
-            ov.z = pack_bf16(f[4], f[5]);
-            ov.w = pack_bf16(f[6], f[7]);
-            xin[i] = ov;
+            xin[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
     }
 }
