@@ -195,7 +195,7 @@ def cpu_baseline(threads=None, budget_s=150.0):
             "extrapolation_factor": factor, "est_step_seconds": est_step_s}
 
 
-CPU_ARM_BUDGET_S = 180.0  # host seconds the timed steps of `--impl reference` may spend on full-N blocks
+CPU_ARM_BUDGET_S = 360.0  # host seconds the timed steps of `--impl reference` may spend on full-N blocks (K <= 3: full-N, ~80 s each on 128 threads)
 
 
 def run_reference_arm(args):
