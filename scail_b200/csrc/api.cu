@@ -286,7 +286,7 @@ int scail_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, cons
     if (use_cg2) {
         if ((rc = make_tmap_2d(A, M, K, lda, 128, GEMM_BK, &ta))) return rc;
         if ((rc = make_tmap_2d(W, N, K, ldw, 128, GEMM_BK, &tw))) return rc;
-        p.group_m = gm_env > 0 ? gm_env : 12;  // in 256-row pairs
+        p.group_m = gm_env > 0 ? gm_env : 16;  // in 256-row pairs (sweep: profiles/r02_gemm_l2.md)
         if ((rc = set_smem(gemm_bf16_cg2_kernel, GEMM2_SMEM_BYTES))) return rc;
         int grid = (int)(2 * pair_tiles < sms ? 2 * pair_tiles : (sms & ~1));
         gemm_bf16_cg2_kernel<<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ta, tw, p);
