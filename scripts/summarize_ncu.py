@@ -42,7 +42,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg.per_second",
         "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
         "lts__t_sector_hit_rate.pct", "sm__cycles_active.avg"]
-for k in ("attn", "gemm", "rows", "conv"):
+for k in ("attn", "gemm", "rows", "rope", "conv"):
     try:
         txt = subprocess.run(["ncu", "-i", f"gpurun_out/{k}_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
