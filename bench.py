@@ -9,8 +9,11 @@ same step through scail_b200.sampler.HostStep (pinned host -> device inputs, dev
 inside the region; `fwd_per_s` (extra key) = value * 2 is the b=1-forward rate BASELINE.md's targets are
 quoted on.  Random-init weights of the 14B architecture, synthetic inputs (no network).
 
-N > 1: one process per GPU (torchrun), context parallel over the token dimension with one NCCL K/V
-all-gather per block (scail_b200.parallel); strong scaling (the step is fixed, ranks split its tokens).
+N > 1: one process per GPU (torchrun); strong scaling (the step is fixed).  Default layout for even N
+(`--parallel auto`): the two CFG branches on the two halves of the ranks, context parallel over the token dimension
+inside each half with one NCCL K/V all-gather per block (scail_b200.parallel.HybridParallel); `--parallel cp` = pure
+context parallel over all ranks.  Every N > 1 line carries `cp_check_rel` (2 blocks of step 0 vs a single-GPU recompute on
+rank 0) and `latent_checksum` (equal to the 1-GPU line's for the same --steps/--warmup).
 
 --impl reference: the reference's own CPU implementation of the path cannot travel to the GPU box
 (/root/reference is absent there), so this arm times the oracle port (oracle/dit_oracle.py, fp32, all host
