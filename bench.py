@@ -502,27 +502,30 @@ def main():
         out["roofline"] = None
         out["note"] = "PyTorch library path (cuBLASLt / flash-cuDNN SDPA / F.layer_norm), baseline/torchlib.py; none of this repo's kernels"
     elif world == 1 and not args.no_extras:
-        from baseline import torchlib
-        with torch.no_grad():
-            xl = d["x"].clone()
-            fn = lambda: torchlib.sampler_step(model, xl, sig[10], sig[11], cond, uc, 4.0)
-            lib_ms = _time_cuda(fn, 2, 1)
-            # parity of the two arms on the bench's own inputs and weights (all 40 blocks, N = 27 904): the DiT velocity of
-            # each CFG branch, ours vs the library chain (both bf16; neither is the fp32 truth)
-            x2 = torch.cat([d["x"], d["x"]], 0)
-            ts = torch.full((2,), float(sig[10]) * 1000.0, device=dev, dtype=torch.float32)
-            ctx = sampler.prepare_context(cond, uc)
-            v_o = model(x2, timesteps=ts, context=ctx, ref_concat=cond["ref_concat"], concat_smpl_render=cond["concat_smpl_render"],
-                        image_clip_features=cond["image_clip_features"]).float()
-            v_l = torchlib.dit_forward(model, x2, ts, ctx, cond["ref_concat"], cond["concat_smpl_render"],
-                                       cond["image_clip_features"]).float()
-            rel = [float((v_o[i] - v_l[i]).norm() / v_l[i].norm()) for i in range(2)]
-            del x2, v_o, v_l
-        out["library_baseline"] = {"steps_per_s": 1000.0 / lib_ms, "ms_per_step": lib_ms, "ours_over_library": lib_ms / ms,
-                                   "what": "the same step (weights, inputs, N, bf16) on the PyTorch library path the reference runs "
-                                           "on a GPU: F.linear (cuBLASLt), F.scaled_dot_product_attention, F.layer_norm; baseline/torchlib.py",
-                                   "velocity_rel_l2_ours_vs_library": {"uncond": rel[0], "cond": rel[1]}}
-        del xl
+        try:  # an extra must never take the headline line down with it
+            from baseline import torchlib
+            with torch.no_grad():
+                xl = d["x"].clone()
+                fn = lambda: torchlib.sampler_step(model, xl, sig[10], sig[11], cond, uc, 4.0)
+                lib_ms = _time_cuda(fn, 2, 1)
+                # parity of the two arms on the bench's own inputs and weights (all 40 blocks, N = 27 904): the DiT velocity of
+                # each CFG branch, ours vs the library chain (both bf16; neither is the fp32 truth)
+                x2 = torch.cat([d["x"], d["x"]], 0)
+                ts = torch.full((2,), float(sig[10]) * 1000.0, device=dev, dtype=torch.float32)
+                ctx = sampler.prepare_context(cond, uc)
+                v_o = model(x2, timesteps=ts, context=ctx, ref_concat=cond["ref_concat"], concat_smpl_render=cond["concat_smpl_render"],
+                            image_clip_features=cond["image_clip_features"]).float()
+                v_l = torchlib.dit_forward(model, x2, ts, ctx, cond["ref_concat"], cond["concat_smpl_render"],
+                                           cond["image_clip_features"]).float()
+                rel = [float((v_o[i] - v_l[i]).norm() / v_l[i].norm()) for i in range(2)]
+                del x2, v_o, v_l
+            out["library_baseline"] = {"steps_per_s": 1000.0 / lib_ms, "ms_per_step": lib_ms, "ours_over_library": lib_ms / ms,
+                                       "what": "the same step (weights, inputs, N, bf16) on the PyTorch library path the reference runs "
+                                               "on a GPU: F.linear (cuBLASLt), F.scaled_dot_product_attention, F.layer_norm; baseline/torchlib.py",
+                                       "velocity_rel_l2_ours_vs_library": {"uncond": rel[0], "cond": rel[1]}}
+            del xl
+        except Exception as e:
+            out["library_baseline"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
         try:  # the same step with the forward captured in a CUDA graph (3 host launches per step)
             with torch.no_grad():
@@ -535,9 +538,12 @@ def main():
         except Exception as e:
             out["cuda_graph"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
-        out["kernel_compare"] = kernel_compare(dev)
-        torch.cuda.empty_cache()
-        out["vae_decode"] = vae_decode_bench(dev, peaks)
+        for key, fn in (("kernel_compare", lambda: kernel_compare(dev)), ("vae_decode", lambda: vae_decode_bench(dev, peaks))):
+            try:  # an extra must never take the headline line down with it
+                out[key] = fn()
+            except Exception as e:
+                out[key] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
     if not args.no_cpu_baseline and world >= 1 and not lib_arm:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
